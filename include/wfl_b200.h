@@ -1,0 +1,182 @@
+/*
+ * wfl_b200.h -- C ABI of libwfl_b200.so: the sm_100a kernels behind WFL-ASR's batched labeling
+ * forward path (audio front-end -> encoder -> BiLSTM -> Conformer -> dilated conv -> BIO head ->
+ * threshold/argmax -> median -> BIO -> HTK .lab segments).
+ *
+ * The reference (usamireko/WFL-ASR) is pure Python and has NO FFI/plugin interface (SURVEY.md
+ * section 8b); its seam is the Python API (REF/model.py BIOPhonemeTagger, REF/infer.py infer_audio,
+ * REF/utils.py decode_bio_tags / merge_adjacent_segments / save_lab).  This header is therefore the
+ * surface a maintainer would bind with ctypes from those files; each entry
+ * point cites the reference lines whose arithmetic it replaces.  REF = reference repo root,
+ * TF = transformers, TORCH = torch.
+ *
+ * Conventions: every function returns 0 (WFL_OK) or a negative error code and never throws or
+ * exits; wfl_last_error() returns a thread-local message.  All pointers are DEVICE pointers unless
+ * named host_*; the caller owns every buffer; all work is enqueued on the caller's stream
+ * (a cudaStream_t passed as void*), with no hidden synchronisation and no internal threads.
+ * There is NO CPU fallback: on a box without an sm_100 GPU the compute entry points fail.
+ */
+#ifndef WFL_B200_H_
+#define WFL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFL_OK 0
+#define WFL_ERR_INVALID_ARGUMENT (-1)
+#define WFL_ERR_CUDA (-2)
+#define WFL_ERR_UNSUPPORTED (-3)
+
+#define WFL_ABI_VERSION 1
+
+/* ---- library ------------------------------------------------------------------------------ */
+int wfl_abi_version(void);
+const char* wfl_last_error(void);
+/* Fills SM count and compute capability of the current device; fails without a CUDA device. */
+int wfl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K7/K2/K4/K12/K14/K16: dense contractions (tcgen05 + TMEM + TMA) ------------------------
+ * One kernel family computes   acc[b, t, n] = sum_s sum_k A[b, t + shift_s, col_s + k] * W[n, s*slab_k + k]
+ * over `num_slabs` K-slabs, i.e. nn.Linear (1 slab), Conv1d k/dilation/padding as shifted slabs
+ * (rows outside [0, a_rows) read as zero = the conv's zero padding), and stride-2 convs through a
+ * paired-row view of A.  Replaces: every nn.Linear / nn.Conv1d of REF/model.py:9-16,26-38,98,
+ * 126-142 and of TF/models/whisper/modeling_whisper.py:567-568 + attention/MLP projections.
+ */
+#define WFL_MAX_SLABS 32
+
+enum wfl_act { WFL_ACT_NONE = 0, WFL_ACT_GELU = 1, WFL_ACT_RELU = 2 };
+enum wfl_out_mode {
+  WFL_OUT_STORE_BF16 = 0, /* out_bf16 = act(acc + bias)                                  */
+  WFL_OUT_STORE_F32 = 1,  /* out_f32  = act(acc + bias)                                  */
+  WFL_OUT_ADD_F32 = 2,    /* out_f32 += alpha * act(acc + bias)   (residual stream)      */
+  WFL_OUT_GLU_BF16 = 3    /* out_bf16[:, j] = (acc_a + b_a) * sigmoid(acc_g + b_g); weights are packed so that
+                             every block of `glu_block` output rows holds glu_block/2 value rows followed by the
+                             matching glu_block/2 gate rows (REF/model.py:31-32)          */
+};
+
+typedef struct wfl_gemm_desc {
+  /* A: bf16, logical [batches][a_rows][a_cols], a_cols contiguous */
+  const void* a;
+  int64_t a_rows, a_cols, a_row_stride, a_batch_stride; /* strides in elements */
+  int32_t batches;
+  /* W: bf16 [n][num_slabs * slab_k], K contiguous */
+  const void* w;
+  int32_t n, slab_k, num_slabs;
+  int32_t slab_row_shift[WFL_MAX_SLABS];
+  int32_t slab_a_col[WFL_MAX_SLABS];
+  /* epilogue */
+  const float* bias;         /* [n] or NULL; with bias_batch_stride != 0: [batches][n] (REF/model.py:176-180 folded) */
+  int64_t bias_batch_stride; /* elements */
+  int32_t act, out_mode;
+  float alpha;
+  void* out; /* bf16 or f32, logical [batches][m_rows][out_cols] */
+  int64_t m_rows, out_row_stride, out_batch_stride; /* elements */
+  int32_t tile_n;                                     /* 0 = auto, else 64/128/256 */
+} wfl_gemm_desc;
+
+int wfl_gemm(const wfl_gemm_desc* desc, void* stream);
+
+/* ---- K9: fused flash attention (tcgen05, online softmax) -------------------------------------
+ * out[b, t, h*hd:(h+1)*hd] = softmax_k(scale * q.k + gate[b,h,t] * rel_bias[h, k - t + T - 1]) v
+ * q/k/v are column slices of one bf16 buffer [B][T][row_stride] (q_col/k_col/v_col = column of
+ * head 0).  rel_bias/gate may be NULL (Whisper TF/.../modeling_whisper.py:284-357; Conformer
+ * nn.MultiheadAttention REF/model.py:26,42); both set = WavLM gated relative position bias
+ * (TF/models/wavlm/modeling_wavlm.py:147-241).
+ */
+int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int32_t q_col, int32_t k_col,
+                  int32_t v_col, int32_t B, int32_t T, int32_t H, int32_t hd, float scale, const float* rel_bias,
+                  const float* gate, void* out, int64_t out_row_stride, int64_t out_batch_stride, void* stream);
+
+/* ---- K8: LayerNorm (fp32 statistics) ----------------------------------------------------------
+ * y = LN(x; gamma, beta); out_f32 (nullable) receives y; out_bf16 (nullable) receives y, or
+ * LN(y; gamma2, beta2) when gamma2 != NULL (REF/model.py:43-44: x = ln1(x + attn); ln2(x)).
+ * out_f32 may alias x.  nn.LayerNorm eps = 1e-5 everywhere on the path.
+ */
+int wfl_layernorm(const float* x, int64_t rows, int32_t d, const float* gamma, const float* beta,
+                  const float* gamma2, const float* beta2, float eps, float* out_f32, void* out_bf16,
+                  void* stream);
+
+/* fp32 [rows][d] -> bf16 [rows][2d] = [hi | lo] with hi = bf16(x), lo = bf16(x - hi): operands for the
+ * split-precision (3-slab) tail GEMMs (classifier REF/model.py:135,192). */
+int wfl_split_bf16(const float* x, int64_t rows, int32_t d, void* out_hi_lo, void* stream);
+
+/* dst[b][t][:] = src[t][:] for b < batches (positional embedding broadcast before the conv2
+ * epilogue accumulates into it; TF/models/whisper/modeling_whisper.py:622-625). */
+int wfl_broadcast_rows(const float* src, int64_t rows, int32_t d, int32_t batches, float* dst, void* stream);
+
+/* out[r][j] = sigmoid(dot(x[r], w[j]) + b[j]), j < n_out <= 4: the 1x1 conv + Sigmoid that ends the
+ * boundary-offset head (REF/model.py:140-141,193).  x bf16 [rows][d], w fp32 [n_out][d]. */
+int wfl_rowdot_sigmoid(const void* x_bf16, int64_t rows, int32_t d, const float* w, const float* b, int32_t n_out,
+                       float* out, void* stream);
+
+/* ---- K0: peak normalisation (REF/infer.py:234-235 and per chunk :114-115) ---------------------
+ * out[i] = (float)(in[i] / (max|in| + 1e-8)) per clip, division in fp64 like the reference's numpy
+ * float64 array.  Clip c covers samples [clip_begin[c], clip_begin[c+1]) of `in`; out rows have
+ * `out_stride` floats and are zero-filled past the clip's length.  out_f64 (nullable) receives the
+ * un-narrowed quotient at the input's flat positions (long files are normalised twice: whole file, then
+ * each 30 s chunk, REF/infer.py:234-235 then :114-115).  `out` may be NULL when only out_f64 is wanted.
+ * scratch_max: [n_clips] doubles.
+ */
+int wfl_peak_normalize(const double* in, const int64_t* clip_begin, int32_t n_clips, float* out,
+                       int64_t out_stride, double* out_f64, double* scratch_max, void* stream);
+
+/* ---- K1: Whisper log-mel front-end (TF/models/whisper/feature_extraction_whisper.py:135-164) --
+ * wave fp32 [B][wave_stride] (n_samples valid, zero-extended/truncated to 480000), windowed DFT as
+ * a direct contraction against basis [402][400] (rows 0..200 cos, 201..401 -sin, periodic Hann folded
+ * in), power, mel (filters [201][n_mels]), log10(clamp 1e-10), per-clip max-8 floor, (x+4)/4.
+ * out bf16 [B][3000][out_stride] (channels >= n_mels zeroed).  scratch: fp32 [B][3000][n_mels] +
+ * B floats (clip maxima).
+ */
+int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, const float* basis,
+                       const float* mel_filters, int32_t n_mels, void* out_bf16, int32_t out_stride,
+                       float* scratch_logspec, float* scratch_max, void* stream);
+
+/* ---- K15/K18/K19: decode -> median -> BIO -> merge --------------------------------------------- */
+typedef struct wfl_segment {
+  double start; /* seconds, fp64 exactly as the reference's Python floats */
+  double end;
+  int32_t ph;   /* phoneme index (label_ph of the run's label) */
+  int32_t pad_;
+} wfl_segment;
+
+enum wfl_label_kind { WFL_TAG_O = 0, WFL_TAG_B = 1, WFL_TAG_I = 2, WFL_TAG_OTHER = 3 };
+enum wfl_merge_mode { WFL_MERGE_NONE = 0, WFL_MERGE_RIGHT = 1, WFL_MERGE_LEFT = 2, WFL_MERGE_PREVIOUS = 3 };
+
+/* REF/infer.py:86-96 + :297: softmax, max-prob < threshold (fp32 compare) -> o_id else argmax
+ * (first maximal index).  logits fp32 [rows][row_stride], L valid columns. */
+int wfl_decode_frames(const float* logits, int64_t rows, int32_t L, int64_t row_stride, int32_t o_id,
+                      float threshold, int32_t* ids, void* stream);
+
+/* scipy.ndimage.median_filter(ids, size=k) per clip (REF/infer.py:298-299): reflect boundary,
+ * window [i-k/2, i-k/2+k-1], sorted element k/2.  ids [n_clips][clip_stride], lengths[c] valid. */
+int wfl_median_filter(const int32_t* ids_in, int32_t* ids_out, const int32_t* lengths, int32_t n_clips,
+                      int64_t clip_stride, int32_t k, void* stream);
+
+/* REF/utils.py:10-74 decode_bio_tags + REF/infer.py:180 time shift: per clip, label ids -> runs ->
+ * (start, end, ph) with fp64 times (idx + offset) * frame_duration (+ time_shift[c]);
+ * offsets fp32 [n_clips][clip_stride][2] or NULL -> (idx + 0.5).  label_kind/label_ph: [n_labels].
+ * segs: [n_clips][clip_stride]; nseg: [n_clips]. */
+int wfl_bio_decode(const int32_t* ids, const float* offsets, const int32_t* lengths, int32_t n_clips,
+                   int64_t clip_stride, const int8_t* label_kind, const int32_t* label_ph, int32_t n_labels,
+                   double frame_duration, const double* time_shift, wfl_segment* segs, int32_t* nseg,
+                   void* stream);
+
+/* REF/utils.py:148-186 merge_adjacent_segments over the concatenation of clips
+ * [file_clip_begin[f], file_clip_begin[f+1]) (REF/infer.py:309-310 merges across 30 s chunks).
+ * ph_class (nullable, [n_ph]) maps phoneme index -> equality class after the canonical_to_lang
+ * remap (REF/infer.py:303-307).  File f's result is written at out[file_clip_begin[f]*clip_stride ...]
+ * with count nout[f]. */
+int wfl_merge_segments(const wfl_segment* segs, const int32_t* nseg, int64_t clip_stride,
+                       const int32_t* file_clip_begin, int32_t n_files, const int32_t* ph_class, int32_t mode,
+                       wfl_segment* out, int32_t* nout, void* stream);
+
+/* REF/utils.py:76-81 save_lab arithmetic: htk[i] = (int64) trunc(t[i] * 1e7) in fp64. */
+int wfl_htk_times(const wfl_segment* segs, int64_t n, int64_t* start_htk, int64_t* end_htk, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFL_B200_H_ */

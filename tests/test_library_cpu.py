@@ -1,0 +1,103 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/wfl_b200.h declares; host-side logic
+(packing, label tables, wav reader, forced alignment, drop-in model state_dict) with no compute calls."""
+import os
+import re
+import struct
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+def test_library_exports_header_symbols():
+    import __graft_entry__ as ge
+    ge.build()
+    from wfl_asr_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "wfl_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(wfl_\w+)\s*\(", header, re.M))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/wfl_b200.h but not exported"
+    bound = set(_lib.SIGNATURES) | set(_lib.NOARG)
+    assert declared <= bound, f"header symbols without a ctypes signature: {declared - bound}"
+    assert lib.wfl_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    from wfl_asr_b200 import ops
+    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    with pytest.raises(ops.WflError):
+        ops.linear(a, a, torch.zeros(128, 128, dtype=torch.bfloat16))
+    from wfl_asr_b200 import utils
+    with pytest.raises(ops.WflError):
+        utils.decode_bio_tags(["O", "B-a"])
+
+
+def test_state_dict_matches_reference_layout():
+    """Strict load of weights laid out by the oracle's key/shape table, which tests/test_oracle_forward.py pins to the
+    reference module's own state_dict."""
+    import make_forward_golden as mfg
+    from wfl_asr_b200.model import BIOPhonemeTagger
+    for name in mfg.CASES:
+        cfg, labels, sd, _, _ = mfg.case_inputs(name)
+        model = BIOPhonemeTagger(cfg, labels)
+        own = model.state_dict()
+        assert set(own) == set(sd), (name, sorted(set(own) ^ set(sd))[:6])
+        for k in sd:
+            assert own[k].shape == sd[k].shape and own[k].dtype == sd[k].dtype, (name, k)
+        model.load_state_dict(sd, strict=True)
+        assert model.label2id["O"] == labels.index("O") and model.encoder_type in ("whisper", "wavlm")
+
+
+def test_model_rejects_bad_encoder_type():
+    from wfl_asr_b200.model import BIOPhonemeTagger
+    from wfl_asr_b200 import synth
+    cfg = synth.workload_config("cfg2")
+    cfg["model"]["encoder_type"] = "hubert"
+    with pytest.raises(ValueError):
+        BIOPhonemeTagger(cfg, ["O"])
+
+
+def test_packing_folds():
+    from wfl_asr_b200 import packing
+    g = torch.Generator().manual_seed(0)
+    w, b = torch.randn(8, 6, 5, generator=g), torch.randn(8, generator=g)
+    gamma, beta = torch.randn(8, generator=g), torch.randn(8, generator=g)
+    mean, var = torch.randn(8, generator=g), torch.rand(8, generator=g) + 0.5
+    x = torch.randn(2, 6, 20, generator=g)
+    ref = torch.nn.functional.batch_norm(torch.nn.functional.conv1d(x, w, b, padding=2), mean, var, gamma, beta, False, 0.0, 1e-5)
+    wf, bf = packing.fold_batchnorm(w, b, gamma, beta, mean, var)
+    assert (torch.nn.functional.conv1d(x, wf, bf, padding=2) - ref).abs().max() < 1e-5
+    taps = packing.conv_taps(w)
+    assert torch.equal(taps.view(8, 5, 6)[:, 3, :], w[:, :, 3])
+    wg, bg = packing.interleave_glu(torch.arange(16.0)[:, None].repeat(1, 3), torch.arange(16.0), 8)
+    assert bg.tolist() == [0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15]
+    w3 = packing.split_hi_lo(torch.randn(4, 8, generator=g))
+    assert w3.shape == (4, 24) and w3.dtype == torch.bfloat16
+
+
+def test_label_tables_and_alignment():
+    from wfl_asr_b200.pipeline import label_tables
+    phon, kind, ph = label_tables(["B-a", "B-k", "I-a", "I-k", "O", "weird"])
+    assert phon == ["a", "k"] and kind == [1, 1, 2, 2, 0, 3] and ph == [0, 1, 0, 1, -1, -1]
+    from wfl_asr_b200.infer import align_phoneme_list, split_audio
+    pred = [(0.0, 0.1, "a"), (0.1, 0.2, "x"), (0.2, 0.3, "k"), (0.3, 0.4, "s")]
+    assert align_phoneme_list(pred, ["a", "k", "q"]) == [(0.0, 0.1, "a"), (0.2, 0.3, "k"), (0.1, 0.2, "q")]
+    assert [len(s) for s in split_audio(np.zeros(16000 * 65), 16000)] == [480000, 480000, 80000]
+
+
+def test_wav_reader(tmp_path):
+    from wfl_asr_b200.infer import _read_wav
+    x = (np.sin(np.arange(1000) * 0.05) * 20000).astype("<i2")
+    p = tmp_path / "a.wav"
+    with open(p, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + x.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16))
+        f.write(b"data" + struct.pack("<I", x.nbytes) + x.tobytes())
+    audio, sr = _read_wav(str(p))
+    assert sr == 16000 and np.array_equal(audio, x.astype(np.float64) / 32768.0)

@@ -1,0 +1,392 @@
+"""GPU (-m gpu): every C-ABI op against a plain torch fp32 statement of the same op / the oracle.
+All calls go through wfl_asr_b200.ops -> ctypes -> libwfl_b200.so."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected on the CPU box, skipped there by -m "not gpu"
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from oracle import postproc_oracle as po  # noqa: E402
+from oracle import torch_oracle as to  # noqa: E402
+from wfl_asr_b200 import ops  # noqa: E402
+
+DEV = torch.device("cuda:0")
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _report(name, got, ref, tol):
+    err = (got.float() - ref.float()).abs()
+    scale = ref.float().abs().max().item()
+    mx = err.max().item()
+    if not (mx <= tol * max(scale, 1e-6)):
+        bad = (err > tol * max(scale, 1e-6)).nonzero()
+        print(f"[{name}] max err {mx:.4g} (scale {scale:.4g}); {bad.shape[0]} / {err.numel()} bad; first {bad[:8].tolist()}")
+        print(f"[{name}] got {got.flatten()[:8].tolist()} ref {ref.flatten()[:8].tolist()}")
+    assert mx <= tol * max(scale, 1e-6), f"{name}: max err {mx} vs scale {scale}"
+
+
+# ----------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("M,K,N", [(128, 64, 256), (300, 128, 256), (1000, 512, 512), (257, 192, 384)])
+def test_gemm_linear_bf16(M, K, N, tile_n):
+    a = _rand(M, K, seed=1).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).bfloat16()
+    bias = _rand(N, seed=3)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.linear(a, w, out, bias=bias, tile_n=tile_n)
+    ref = a.float() @ w.float().T + bias
+    _report("linear", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("act", [ops.ACT_GELU, ops.ACT_RELU])
+def test_gemm_activations(act):
+    M, K, N = 384, 256, 512
+    a = _rand(M, K, seed=4).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=5).bfloat16()
+    bias = _rand(N, seed=6)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.linear(a, w, out, bias=bias, act=act)
+    pre = a.float() @ w.float().T + bias
+    ref = F.gelu(pre) if act == ops.ACT_GELU else F.relu(pre)
+    _report("act", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("tile_n", [128, 256])
+def test_gemm_f32_store_and_add(tile_n):
+    M, K, N = 500, 128, 256
+    a = _rand(M, K, seed=7).bfloat16()
+    w = _rand(N, K, scale=K ** -0.5, seed=8).bfloat16()
+    bias = _rand(N, seed=9)
+    ref = a.float() @ w.float().T + bias
+    out = torch.empty(M, N, device=DEV)
+    ops.linear(a, w, out, bias=bias, out_mode=ops.OUT_STORE_F32, tile_n=tile_n)
+    _report("store_f32", out, ref, 1e-5)
+    resid = _rand(M, N, seed=10)
+    x = resid.clone()
+    ops.linear(a, w, x, bias=bias, out_mode=ops.OUT_ADD_F32, alpha=0.5, tile_n=tile_n)
+    _report("add_f32", x, resid + 0.5 * ref, 1e-5)
+
+
+def test_gemm_glu():
+    M, K, d = 300, 128, 256
+    a = _rand(M, K, seed=11).bfloat16()
+    w = _rand(2 * d, K, scale=K ** -0.5, seed=12).bfloat16()
+    bias = _rand(2 * d, seed=13)
+    from wfl_asr_b200.packing import interleave_glu
+    wp, bp = interleave_glu(w, bias, 256)
+    out = torch.empty(M, d, device=DEV, dtype=torch.bfloat16)
+    ops.linear(a, wp, out, bias=bp, out_mode=ops.OUT_GLU_BF16, tile_n=256)
+    pre = a.float() @ w.float().T + bias
+    ref = pre[:, :d] * torch.sigmoid(pre[:, d:])
+    _report("glu", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("ksize,dil", [(3, 1), (31, 1), (3, 2), (3, 4)])
+def test_gemm_conv1d(ksize, dil):
+    """Conv1d(C, N, k, dilation, padding=dil*(k-1)//2) over [B, T, C] as shifted K-slabs."""
+    B, T, C, N = 3, 200, 128, 256
+    x = _rand(B, T, C, seed=14).bfloat16()
+    wt = _rand(N, C, ksize, scale=(C * ksize) ** -0.5, seed=15).bfloat16()
+    bias = _rand(N, seed=16)
+    pad = dil * (ksize - 1) // 2
+    w2 = wt.permute(0, 2, 1).contiguous().view(N, ksize * C)  # [N][tap][C]
+    out = torch.empty(B, T, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, w2, out, n=N, slab_k=C, shifts=[j * dil - pad for j in range(ksize)], cols=[0] * ksize, a_rows=T,
+             a_cols=C, a_row_stride=C, a_batch_stride=T * C, batches=B, m_rows=T, out_row_stride=N,
+             out_batch_stride=T * N, bias=bias)
+    ref = F.conv1d(x.float().transpose(1, 2), wt.float(), bias, padding=pad, dilation=dil).transpose(1, 2)
+    _report("conv1d", out, ref, 1e-2)
+
+
+def test_gemm_conv_stride2():
+    """Whisper conv2 (k3, s2, p1) through the paired-row view [T/2, 2C]."""
+    B, T, C, N = 2, 300, 128, 256
+    x = _rand(B, T, C, seed=17).bfloat16()
+    wt = _rand(N, C, 3, scale=(3 * C) ** -0.5, seed=18).bfloat16()
+    bias = _rand(N, seed=19)
+    w2 = wt.permute(0, 2, 1).contiguous().view(N, 3 * C)
+    To = T // 2
+    out = torch.empty(B, To, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, w2, out, n=N, slab_k=C, shifts=[-1, 0, 0], cols=[C, 0, C], a_rows=To, a_cols=2 * C,
+             a_row_stride=2 * C, a_batch_stride=T * C, batches=B, m_rows=To, out_row_stride=N,
+             out_batch_stride=To * N, bias=bias, act=ops.ACT_GELU)
+    ref = F.gelu(F.conv1d(x.float().transpose(1, 2), wt.float(), bias, stride=2, padding=1)).transpose(1, 2)
+    _report("conv_s2", out, ref, 1e-2)
+
+
+def test_gemm_batched_bias_and_split_precision():
+    B, T, d, N = 3, 150, 128, 64
+    x = _rand(B, T, d, seed=20)
+    w = _rand(N, d, scale=d ** -0.5, seed=21)
+    bias = _rand(B, N, seed=22)
+    hl = torch.empty(B, T, 2 * d, device=DEV, dtype=torch.bfloat16)
+    ops.split_bf16(x, hl)
+    assert torch.equal(hl[..., :d], x.bfloat16())
+    w_hi = w.bfloat16()
+    w_lo = (w - w_hi.float()).bfloat16()
+    w3 = torch.cat([w_hi, w_hi, w_lo], dim=1).contiguous()
+    out = torch.empty(B, T, N, device=DEV)
+    ops.gemm(hl, w3, out, n=N, slab_k=d, shifts=[0, 0, 0], cols=[0, d, 0], a_rows=T, a_cols=2 * d, a_row_stride=2 * d,
+             a_batch_stride=T * 2 * d, batches=B, m_rows=T, out_row_stride=N, out_batch_stride=T * N, bias=bias,
+             bias_batch_stride=N, out_mode=ops.OUT_STORE_F32, tile_n=128)
+    ref = x @ w.T + bias[:, None, :]
+    _report("split3", out, ref, 2e-4)
+
+
+def test_gemm_rejects_bad_arguments():
+    a = torch.zeros(128, 100, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(64, 100, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ops.WflError):
+        ops.linear(a, w, out)  # K not a multiple of 64
+
+
+# ----------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, B, T, H, hd, scale, bias=None):
+    d = H * hd
+    q, k, v = qkv.float().split(d, dim=-1)
+    q = q.view(B, T, H, hd).transpose(1, 2)
+    k = k.view(B, T, H, hd).transpose(1, 2)
+    v = v.view(B, T, H, hd).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if bias is not None:
+        s = s + bias
+    return (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, T, d)
+
+
+@pytest.mark.parametrize("hd,H,T,B", [(64, 2, 128, 1), (64, 3, 300, 2), (64, 8, 1500, 1), (256, 2, 200, 2),
+                                       (256, 2, 1500, 1), (384, 2, 333, 1)])
+def test_attention(hd, H, T, B):
+    d = H * hd
+    qkv = _rand(B, T, 3 * d, seed=23).bfloat16()
+    out = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=scale, q_col=0, k_col=d, v_col=2 * d)
+    ref = _attn_ref(qkv, B, T, H, hd, scale)
+    _report(f"attention hd{hd}", out, ref, 2e-2)
+
+
+def test_attention_peaky_scores_rescale():
+    """Large score range forces the lazy O-rescale path (running max grows by > 2^8 between tiles)."""
+    hd, H, T, B = 64, 2, 700, 1
+    d = H * hd
+    qkv = _rand(B, T, 3 * d, seed=24)
+    qkv[..., :2 * d] *= 3.0
+    ramp = torch.linspace(0.2, 3.0, T, device=DEV)[None, :, None]
+    qkv[..., d:2 * d] *= ramp  # later keys score higher -> max keeps growing
+    qkv = qkv.bfloat16()
+    out = torch.empty(B, T, d, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=1.0, q_col=0, k_col=d, v_col=2 * d)
+    _report("attention rescale", out, _attn_ref(qkv, B, T, H, hd, 1.0), 2e-2)
+
+
+def test_attention_wavlm_bias():
+    hd, H, T, B = 64, 4, 260, 2
+    d = H * hd
+    qkv = _rand(B, T, 3 * d, seed=25).bfloat16()
+    emb = _rand(320, H, seed=26)
+    gate = (torch.rand(B, H, T, generator=torch.Generator().manual_seed(27)) * 2).to(DEV)
+    buckets = to.wavlm_rel_buckets(T).to(DEV)
+    pos_bias = emb[buckets].permute(2, 0, 1)  # [H, T(q), T(k)]
+    rel = torch.arange(-(T - 1), T, device=DEV)
+    nb, max_exact = 160, 80
+    # table over rel = k - q in [-(T-1), T-1]
+    qi = torch.zeros(2 * T - 1, dtype=torch.long, device=DEV)
+    table = torch.empty(H, 2 * T - 1, device=DEV)
+    for r in range(-(T - 1), T):
+        q_, k_ = (0, r) if r >= 0 else (-r, 0)
+        table[:, r + T - 1] = pos_bias[:, q_, k_]
+    out = torch.empty(B, T, d, device=DEV, dtype=torch.bfloat16)
+    scale = hd ** -0.5
+    ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=scale, q_col=0, k_col=d, v_col=2 * d,
+                  rel_bias=table.contiguous(), gate=gate.contiguous())
+    ref = _attn_ref(qkv, B, T, H, hd, scale, bias=gate[..., None] * pos_bias[None])
+    _report("attention wavlm", out, ref, 2e-2)
+
+
+# ----------------------------------------------------------------------------------------- row ops
+@pytest.mark.parametrize("d", [512, 768, 1280])
+def test_layernorm(d):
+    rows = 1003
+    x = _rand(rows, d, scale=2.0, seed=28) + 0.5
+    g1, b1, g2, b2 = _rand(d, seed=29), _rand(d, seed=30), _rand(d, seed=31), _rand(d, seed=32)
+    ref1 = F.layer_norm(x, (d,), g1, b1, 1e-5)
+    ref2 = F.layer_norm(ref1, (d,), g2, b2, 1e-5)
+    o32 = torch.empty_like(x)
+    o16 = torch.empty(rows, d, device=DEV, dtype=torch.bfloat16)
+    ops.layernorm(x, g1, b1, out_f32=o32, out_bf16=o16)
+    _report("ln f32", o32, ref1, 2e-6)
+    _report("ln bf16", o16, ref1, 8e-3)
+    ops.layernorm(x, g1, b1, out_f32=o32, out_bf16=o16, gamma2=g2, beta2=b2)
+    _report("ln2 bf16", o16, ref2, 8e-3)
+    xin = x.clone()
+    ops.layernorm(xin, g1, b1, out_f32=xin)  # in place
+    _report("ln inplace", xin, ref1, 2e-6)
+
+
+def test_broadcast_and_rowdot():
+    src = _rand(150, 64, seed=33)
+    dst = torch.empty(3, 150, 64, device=DEV)
+    ops.broadcast_rows(src, dst, 3)
+    assert torch.equal(dst, src[None].expand(3, -1, -1))
+    x = _rand(777, 512, seed=34).bfloat16()
+    w, b = _rand(2, 512, scale=0.05, seed=35), _rand(2, seed=36)
+    out = torch.empty(777, 2, device=DEV)
+    ops.rowdot_sigmoid(x, w, b, out)
+    _report("rowdot", out, torch.sigmoid(x.float() @ w.T + b), 1e-5)
+
+
+def test_peak_normalize_bit_exact():
+    lens = [16000, 1, 48011, 480000]
+    rng = np.random.default_rng(5)
+    clips = [rng.standard_normal(n) * s for n, s in zip(lens, (0.3, 2.0, 1e-3, 0.7))]
+    flat = torch.from_numpy(np.concatenate(clips)).to(DEV)
+    begin = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=DEV)
+    out = torch.full((len(lens), 480000), float("nan"), device=DEV)
+    scratch = torch.empty(len(lens), dtype=torch.float64, device=DEV)
+    ops.peak_normalize(flat, begin, len(lens), out, scratch)
+    for i, c in enumerate(clips):
+        ref = po.peak_normalize(c).astype(np.float32)  # REF/infer.py:234-235 then float32 tensor (:251)
+        got = out[i].cpu().numpy()
+        assert np.array_equal(got[:len(c)], ref)
+        assert not got[len(c):].any()
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_whisper_logmel(n_mels):
+    from wfl_asr_b200.frontend import whisper_frontend_constants
+    B = 3
+    waves = [torch.from_numpy(to.synth_wave(40 + i, s)).float() for i, s in enumerate((30.0, 3.7, 11.0))]
+    wave = torch.zeros(B, 480000)
+    for i, w in enumerate(waves):
+        wave[i, :len(w)] = w
+    basis, filt = whisper_frontend_constants(n_mels, DEV)
+    out = torch.empty(B, 3000, 128, device=DEV, dtype=torch.bfloat16)
+    s1 = torch.empty(B, 3000, n_mels, device=DEV)
+    s2 = torch.empty(B, device=DEV)
+    ops.whisper_logmel(wave.to(DEV), 480000, basis, filt, n_mels, out, s1, s2)
+    ref = to.whisper_log_mel(wave, n_mels).transpose(1, 2)  # [B, 3000, n_mels]
+    got = out[..., :n_mels].float().cpu()
+    assert not out[..., n_mels:].any()
+    # fp32 log-mel before the bf16 rounding of the output: check the scratch against the oracle pre-normalisation
+    err = (got - ref).abs().max().item()
+    assert err <= 1.2e-2, err  # bf16 rounding of values in [-1, 2]
+    lo = s1.cpu()
+    mx = lo.amax(dim=(1, 2), keepdim=True)
+    renorm = (torch.maximum(lo, mx - 8.0) + 4.0) / 4.0
+    assert (renorm - ref).abs().max().item() <= 2e-4
+
+
+# ----------------------------------------------------------------------------------------- post-processing
+def _label_tables(labels):
+    phon, kind, ph = [], [], []
+    for t in labels:
+        if t == "O":
+            kind.append(0); ph.append(-1)
+        elif t.startswith("B-") or t.startswith("I-"):
+            name = t[2:]
+            if name not in phon:
+                phon.append(name)
+            kind.append(1 if t[0] == "B" else 2); ph.append(phon.index(name))
+        else:
+            kind.append(3); ph.append(-1)
+    return phon, torch.tensor(kind, dtype=torch.int8, device=DEV), torch.tensor(ph, dtype=torch.int32, device=DEV)
+
+
+def _segs_from_device(segs, n, phon):
+    raw = segs.cpu().numpy().view(np.dtype([("s", "<f8"), ("e", "<f8"), ("ph", "<i4"), ("pad", "<i4")]))
+    return [(float(raw["s"][i]), float(raw["e"][i]), phon[int(raw["ph"][i])]) for i in range(n)]
+
+
+def test_decode_frames_golden(golden):
+    labels = golden["labels"]
+    o_id = labels.index("O")
+    for rec in golden["suppress"]:
+        lg = torch.tensor(rec["logits"], dtype=torch.float32, device=DEV)
+        ids = torch.empty(lg.shape[0], dtype=torch.int32, device=DEV)
+        ops.decode_frames(lg, lg.shape[1], o_id, rec["threshold"], ids)
+        assert ids.cpu().tolist() == rec["ids"]
+
+
+def test_median_golden(golden):
+    for rec in golden["median"]:
+        ids = torch.tensor([rec["ids"]], dtype=torch.int32, device=DEV)
+        out = torch.empty_like(ids)
+        ln = torch.tensor([len(rec["ids"])], dtype=torch.int32, device=DEV)
+        ops.median_filter(ids, out, ln, rec["k"])
+        assert out[0].cpu().tolist() == rec["out"], rec["k"]
+
+
+def test_bio_decode_merge_lab_golden(golden):
+    labels = golden["labels"]
+    phon, kind, ph = _label_tables(labels)
+    recs = [r for r in golden["decode"] if len(r["tags"]) > 0]
+    stride = max(len(r["tags"]) for r in recs)
+    n = len(recs)
+    ids = torch.zeros(n, stride, dtype=torch.int32)
+    offs = torch.zeros(n, stride, 2)
+    for i, r in enumerate(recs):
+        ids[i, :len(r["tags"])] = torch.tensor([labels.index(t) for t in r["tags"]], dtype=torch.int32)
+    lens = torch.tensor([len(r["tags"]) for r in recs], dtype=torch.int32, device=DEV)
+    segs = torch.zeros(n, stride, 24, dtype=torch.uint8, device=DEV)
+    nseg = torch.zeros(n, dtype=torch.int32, device=DEV)
+    for with_off in (True, False):
+        sel = [i for i, r in enumerate(recs) if (r["offsets"] is not None) == with_off]
+        if with_off:
+            for i in sel:
+                offs[i, :len(recs[i]["tags"])] = torch.tensor(recs[i]["offsets"])
+        ops.bio_decode(ids.to(DEV), offs.to(DEV) if with_off else None, lens, kind, ph, 0.02, None, segs, nseg)
+        counts = nseg.cpu().tolist()
+        for i in sel:
+            got = _segs_from_device(segs[i], counts[i], phon)
+            assert got == [(s, e, p) for s, e, p in recs[i]["segments"]], i  # exact fp64 equality
+        fcb = torch.arange(n + 1, dtype=torch.int32, device=DEV)
+        for mode in ("right", "left", "previous", "none"):
+            out = torch.zeros_like(segs)
+            nout = torch.zeros(n, dtype=torch.int32, device=DEV)
+            ops.merge_segments(segs, nseg, stride, fcb, n, None, mode, out, nout)
+            oc = nout.cpu().tolist()
+            for i in sel:
+                got = _segs_from_device(out[i], oc[i], phon)
+                assert got == [(s, e, p) for s, e, p in recs[i]["merged"][mode]], (i, mode)
+                s_h = torch.empty(max(oc[i], 1), dtype=torch.int64, device=DEV)
+                e_h = torch.empty_like(s_h)
+                ops.htk_times(out[i], oc[i], s_h, e_h)
+                lab = "".join(f"{a} {b} {p}\n" for a, b, (_, _, p) in zip(s_h.cpu().tolist(), e_h.cpu().tolist(), got))
+                assert lab == recs[i]["lab"][mode]
+
+
+def test_chunked_merge_golden(golden):
+    labels = golden["labels"]
+    phon, kind, ph = _label_tables(labels)
+    for rec in golden["chunk"]:
+        nc = len(rec["chunks"])
+        ids = torch.tensor([[labels.index(t) for t in ch["tags"]] for ch in rec["chunks"]], dtype=torch.int32, device=DEV)
+        offs = torch.tensor([ch["offsets"] for ch in rec["chunks"]], dtype=torch.float32, device=DEV)
+        lens = torch.full((nc,), 1500, dtype=torch.int32, device=DEV)
+        shift = torch.tensor([ch["current_time"] for ch in rec["chunks"]], dtype=torch.float64, device=DEV)
+        segs = torch.zeros(nc, 1500, 24, dtype=torch.uint8, device=DEV)
+        nseg = torch.zeros(nc, dtype=torch.int32, device=DEV)
+        ops.bio_decode(ids, offs, lens, kind, ph, 0.02, shift, segs, nseg)
+        fcb = torch.tensor([0, nc], dtype=torch.int32, device=DEV)
+        for mode in ("right", "left", "previous", "none"):
+            out = torch.zeros_like(segs)
+            nout = torch.zeros(1, dtype=torch.int32, device=DEV)
+            ops.merge_segments(segs, nseg, 1500, fcb, 1, None, mode, out, nout)
+            got = _segs_from_device(out.view(-1, 24), int(nout.item()), phon)
+            assert got == [(s, e, p) for s, e, p in rec["merged"][mode]], mode
+
+
+def test_merge_rejects_bad_mode():
+    with pytest.raises(ValueError):
+        ops.merge_segments(None, None, 0, None, 0, None, "sideways", None, None)

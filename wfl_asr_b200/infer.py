@@ -1,0 +1,383 @@
+"""Drop-in for the reference's ``infer.py`` entry point (REF/infer.py): same functions, arguments, CLI flags
+and ``.lab`` output, but the model is built once, clips are batched, and everything between the waveform
+and the segment list runs on the GPU (csrc/*.cu via pipeline.Labeler).
+
+Differences that are deliberate and documented in DESIGN.md:
+  * the model is constructed/loaded once per process, not once per file (REF/infer.py:204-208 per file);
+  * no autograd graph is built (the reference never disables grad);
+  * ``--sample/--top-k/--top-p/--temperature`` are accepted and validated like the reference, and like the
+    reference they do not affect the output (REF/infer.py:283-297 overwrites the sampled ids).
+"""
+import os
+import struct
+import sys
+
+import numpy as np
+import torch
+import yaml
+
+from . import ops
+from .model import BIOPhonemeTagger
+from .pipeline import FRAME_DURATION, Labeler
+from .utils import (canonical_to_lang, load_langs, load_phoneme_list, load_phoneme_merge_map, save_lab)
+
+frame_duration = FRAME_DURATION
+MAX_SEGMENT_DURATION = 30.0
+
+
+def load_config(config_path="config.yaml"):
+    with open(config_path, "r") as f:
+        return yaml.safe_load(f)
+
+
+def split_audio(audio, sr, max_duration=MAX_SEGMENT_DURATION):
+    """REF/infer.py:19-28: consecutive chunks of at most ``max_duration`` seconds, no overlap."""
+    step = int(max_duration * sr)
+    return [audio[s:min(s + step, len(audio))] for s in range(0, len(audio), step)]
+
+
+def align_phoneme_list(segments_pred, forced_list):
+    """REF/infer.py:30-60: map a forced phoneme sequence onto predicted segments (greedy in-order label match,
+    then fill the unmatched forced entries with the unused predictions in order).  Host-side list logic."""
+    taken = set()
+    assigned = [None] * len(forced_list)
+    cursor = 0
+    for fi, want in enumerate(forced_list):
+        for pi in range(cursor, len(segments_pred)):
+            if pi not in taken and segments_pred[pi][2] == want:
+                assigned[fi] = pi
+                taken.add(pi)
+                cursor = pi + 1
+                break
+    free = 0
+    for fi in range(len(forced_list)):
+        if assigned[fi] is None:
+            while free < len(segments_pred) and free in taken:
+                free += 1
+            if free < len(segments_pred):
+                assigned[fi] = free
+                taken.add(free)
+                free += 1
+    out = []
+    for fi, want in enumerate(forced_list):
+        pi = assigned[fi]
+        if pi is not None and pi < len(segments_pred):
+            out.append((segments_pred[pi][0], segments_pred[pi][1], want))
+    return out
+
+
+def suppress_low_confidence(logits, id2label, threshold=0.5):
+    """REF/infer.py:86-96 on a [T, L] logits tensor -> list of tag strings (runs wfl_decode_frames)."""
+    lg = logits.float().cuda().contiguous()
+    o_id = [k for k, v in id2label.items() if v == "O"]
+    if not o_id:
+        raise KeyError("O")
+    ids = torch.empty(lg.shape[0], dtype=torch.int32, device=lg.device)
+    ops.decode_frames(lg, lg.shape[1], o_id[0], float(threshold), ids)
+    return [id2label[i] for i in ids.cpu().tolist()]
+
+
+def read_audio(path):
+    """Returns (float64 samples [N] mono, sample_rate).  Uses soundfile when installed (as the reference does,
+    REF/infer.py:217); otherwise a built-in RIFF/WAVE reader for PCM 8/16/24/32 and IEEE float 32/64."""
+    try:
+        import soundfile as sf
+        audio, sr = sf.read(path)
+    except ImportError:
+        audio, sr = _read_wav(path)
+    audio = np.asarray(audio, dtype=np.float64)
+    if audio.ndim == 2:
+        audio = audio.mean(axis=1)
+    return audio, int(sr)
+
+
+def _read_wav(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise ValueError(f"{path}: not a RIFF/WAVE file")
+    pos, fmt, pcm = 12, None, None
+    while pos + 8 <= len(data):
+        cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
+        body = data[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", body[:16])
+            if fmt[0] == 0xFFFE and len(body) >= 26:  # WAVE_FORMAT_EXTENSIBLE: real tag is in the sub-format GUID
+                fmt = (struct.unpack("<H", body[24:26])[0],) + fmt[1:]
+        elif cid == b"data":
+            pcm = body
+        pos += 8 + size + (size & 1)
+    if fmt is None or pcm is None:
+        raise ValueError(f"{path}: missing fmt/data chunk")
+    tag, ch, sr, _, _, bits = fmt
+    if tag == 1:
+        if bits == 8:
+            x = (np.frombuffer(pcm, dtype=np.uint8).astype(np.float64) - 128.0) / 128.0
+        elif bits == 16:
+            x = np.frombuffer(pcm, dtype="<i2").astype(np.float64) / 32768.0
+        elif bits == 24:
+            b = np.frombuffer(pcm[:len(pcm) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+            v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            x = (v - ((v & 0x800000) << 1)).astype(np.float64) / 8388608.0
+        elif bits == 32:
+            x = np.frombuffer(pcm, dtype="<i4").astype(np.float64) / 2147483648.0
+        else:
+            raise ValueError(f"{path}: unsupported PCM width {bits}")
+    elif tag == 3:
+        x = np.frombuffer(pcm, dtype="<f4" if bits == 32 else "<f8").astype(np.float64)
+    else:
+        raise ValueError(f"{path}: unsupported WAVE format tag {tag}")
+    if ch > 1:
+        x = x[:len(x) // ch * ch].reshape(-1, ch)
+    return x, sr
+
+
+class _Session:
+    """Model + labeler built once per (config, checkpoint, device)."""
+    _cache = {}
+
+    def __init__(self, config_path, checkpoint_path, device):
+        self.config = load_config(config_path)
+        save_dir = self.config["output"]["save_dir"]
+        self.labels = load_phoneme_list(os.path.join(save_dir, "phonemes.txt"))
+        self.lang2id = load_langs(os.path.join(save_dir, "langs.txt"))
+        mm_path = os.path.join(save_dir, "phoneme_merge_map.json")
+        self.merge_map = load_phoneme_merge_map(mm_path) if os.path.exists(mm_path) else None
+        if not str(device).startswith("cuda") or not torch.cuda.is_available():
+            raise RuntimeError("wfl_asr_b200 runs on a CUDA device only (no CPU path); got device=%r" % (device,))
+        self.device = torch.device(device)
+        model = BIOPhonemeTagger(self.config, self.labels)
+        state_dict = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
+        model.load_state_dict(state_dict)
+        self.model = model.to(self.device).eval()
+        pp = self.config["postprocess"]
+        self.labeler = Labeler(self.model, median_filter=pp["median_filter"], merge_mode=pp["merge_segments"])
+
+    @classmethod
+    def get(cls, config_path, checkpoint_path, device):
+        key = (os.path.abspath(config_path), os.path.abspath(checkpoint_path), str(device),
+               os.path.getmtime(checkpoint_path), os.path.getmtime(config_path))
+        if key not in cls._cache:
+            cls._cache = {key: cls(config_path, checkpoint_path, device)}
+        return cls._cache[key]
+
+
+def _normalised_clips(audio, sr, dev):
+    """REF/infer.py:234-244 + :113-115: whole-file peak normalisation, split into <= 30 s chunks when longer, each
+    chunk normalised again by its own peak.  Returns (fp32 [n_clips, width] device tensor, chunk lengths)."""
+    n = len(audio)
+    flat = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float64)).to(dev)
+    scratch = torch.empty(64, dtype=torch.float64, device=dev)
+    if n / sr > MAX_SEGMENT_DURATION:
+        step = int(MAX_SEGMENT_DURATION * sr)
+        lens = [min(step, n - s) for s in range(0, n, step)]
+        whole = torch.empty_like(flat)
+        ops.peak_normalize(flat, torch.tensor([0, n], dtype=torch.int64, device=dev), 1, None, scratch, out_f64=whole)
+        begins = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=dev)
+        if len(lens) > scratch.numel():
+            scratch = torch.empty(len(lens), dtype=torch.float64, device=dev)
+        out = torch.empty(len(lens), step, device=dev)
+        ops.peak_normalize(whole, begins, len(lens), out, scratch)
+        return out, lens, True
+    out = torch.empty(1, n, device=dev)
+    ops.peak_normalize(flat, torch.tensor([0, n], dtype=torch.int64, device=dev), 1, out, scratch)
+    return out, [n], False
+
+
+def _forward_clips(sess, clips, lens, lang_id):
+    """Runs the model over clips (rows of a padded fp32 tensor).  Whisper pads/truncates every clip to 30 s itself;
+    WavLM is length-sensitive (no attention mask in the reference), so its clips are run
+    at their exact lengths, grouping equal lengths into one batch."""
+    model, dev = sess.model, sess.device
+    lang_ids = [lang_id] if lang_id is not None else list(sess.lang2id.values())
+    if lang_id is not None and lang_id > max(sess.lang2id.values()):
+        raise ValueError(f"Error: Language ID ({lang_id}) is higher than the latest ID ({max(sess.lang2id.values())}) "
+                         f"of this model.\n Languages and Codes available: {sess.lang2id}")
+    groups = {}
+    if model.encoder_type == "whisper":
+        groups[None] = list(range(len(lens)))
+    else:
+        for i, ln in enumerate(lens):
+            groups.setdefault(ln, []).append(i)
+    logits_out, offsets_out = [None] * len(lens), [None] * len(lens)
+    for ln, idx in groups.items():
+        wave = clips[idx] if ln is None else clips[idx, :ln].contiguous()
+        acc_l = acc_o = None
+        for lid in lang_ids:  # REF/infer.py:265-276: mean over languages when --lang-id is unset
+            lt = torch.full((len(idx),), lid, dtype=torch.long, device=dev)
+            lg, of = model(wave, lt)
+            lg, of = lg.clone(), of.clone()
+            acc_l = lg if acc_l is None else acc_l + lg
+            acc_o = of if acc_o is None else acc_o + of
+        if len(lang_ids) > 1:
+            acc_l, acc_o = acc_l / len(lang_ids), acc_o / len(lang_ids)
+        for j, i in enumerate(idx):
+            logits_out[i], offsets_out[i] = acc_l[j], acc_o[j]
+    return logits_out, offsets_out
+
+
+def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_model.pt",
+                output_lab_path=None, device="cuda", lang_id=None,
+                sample=False, top_k=0, top_p=0.0, temperature=1.0,
+                confidence_threshold=0.0):
+    """REF/infer.py:186-328."""
+    sess = _Session.get(config_path, checkpoint_path, device)
+    config, dev = sess.config, sess.device
+    lang_name = None
+    if lang_id is not None:
+        for n, i in sess.lang2id.items():
+            if i == lang_id:
+                lang_name = n
+                break
+    forced = None
+    phoneme_txt = audio_path.replace(".wav", ".txt")
+    if os.path.exists(phoneme_txt):
+        forced = []
+        with open(phoneme_txt, "r", encoding="utf-8") as f:
+            for line in f:
+                forced.extend(line.strip().split())
+        print(f"Loaded forced phoneme list with {len(forced)} phonemes.")
+
+    audio, sr = read_audio(audio_path)
+    target_sr = config["data"]["sample_rate"]
+    if sr != target_sr:
+        import torchaudio
+        audio = torchaudio.functional.resample(torch.tensor(audio), orig_freq=sr, new_freq=target_sr).numpy()
+        sr = target_sr
+    if len(audio) == 0:
+        raise ValueError(f"{audio_path}: empty audio")
+
+    clips, lens, chunked = _normalised_clips(audio, sr, dev)
+    if chunked:
+        print(f"Audio is too long ({len(audio)/sr:.1f}s), splitting...")
+    logits, offsets = _forward_clips(sess, clips, lens, lang_id)
+
+    labeler = sess.labeler
+    labeler.threshold = float(confidence_threshold)
+    names = None
+    if sess.merge_map and lang_name:  # REF/infer.py:303-307 remap before merging
+        names = [canonical_to_lang(p, lang_name, sess.merge_map) for p in labeler.phon]
+    labeler.set_output_names(names)
+    # every clip of one encoder call has the same T for Whisper; WavLM chunks may differ -> pad to the longest
+    T = max(l.shape[0] for l in logits)
+    n = len(lens)
+    lg = torch.zeros(n, T, logits[0].shape[-1], device=dev)
+    of = torch.zeros(n, T, 2, device=dev)
+    tl = []
+    for i in range(n):
+        lg[i, :logits[i].shape[0]] = logits[i]
+        of[i, :offsets[i].shape[0]] = offsets[i]
+        tl.append(logits[i].shape[0])
+    shifts, t = [], 0.0
+    for ln in lens:  # REF/infer.py:180-182
+        shifts.append(t)
+        t += ln / sr
+    _, merged, nout, fcb, n_files = labeler.postprocess(
+        lg, of, torch.tensor(tl, dtype=torch.int32, device=dev),
+        torch.tensor([0, n], dtype=torch.int32, device=dev),
+        torch.tensor(shifts, dtype=torch.float64, device=dev) if chunked else None)
+    segments_pred = labeler.fetch(merged, nout, fcb, n_files, T)[0]
+
+    if forced is not None:
+        aligned = align_phoneme_list(segments_pred, forced)
+        if "SP" not in forced and "AP" not in forced:
+            before = [s for s in segments_pred if s[2] in ("SP", "AP") and s[1] <= aligned[0][0]]
+            after = [s for s in segments_pred if s[2] in ("SP", "AP") and s[0] >= aligned[-1][1]]
+            segments_pred = before + aligned + after
+        else:
+            segments_pred = aligned
+
+    if output_lab_path:
+        dir_path = os.path.dirname(output_lab_path)
+        if dir_path:
+            os.makedirs(dir_path, exist_ok=True)
+        save_lab(output_lab_path, segments_pred)
+        print(f"Predictions saved to: {output_lab_path}")
+    return segments_pred
+
+
+def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_path: str = "best_model.pt",
+                 output_dir: str = "outputs", device: str = "cuda", lang_id: int = None,
+                 sample=False, top_k=0, top_p=0.0, temperature=1.0, confidence_threshold=0.0):
+    """REF/infer.py:330-357."""
+    wav_files = [f for f in os.listdir(folder_path) if f.lower().endswith(".wav")]
+    os.makedirs(output_dir, exist_ok=True)
+    for wav_file in wav_files:
+        full_audio_path = os.path.join(folder_path, wav_file)
+        output_lab_path = os.path.join(output_dir, wav_file.replace(".wav", ".lab"))
+        print(f"\nInferencing: {wav_file}")
+        segments = infer_audio(audio_path=str(full_audio_path), config_path=str(config_path),
+                               checkpoint_path=str(checkpoint_path), output_lab_path=str(output_lab_path),
+                               device=device, lang_id=lang_id, sample=sample, top_k=top_k, top_p=top_p,
+                               temperature=temperature, confidence_threshold=confidence_threshold)
+        print("Predicted segments:")
+        for start, end, ph in segments:
+            print(f"({round(start, 2)}, {round(end, 2)}, {ph})")
+
+
+def _cli():
+    import click
+    from pathlib import Path
+
+    @click.command(help='Infer with WFL')
+    @click.argument('path', metavar='PATH')
+    @click.option('--checkpoint', '-ckpt', type=str, required=True, help='Path to WFL Checkpoint.')
+    @click.option('--config', '-c', type=str, required=True, help='Path to Config file.')
+    @click.option('--output', '-o', type=str, required=False, default=".", help='Path to output labels.')
+    @click.option('--lang-id', '-l', type=int, required=False, default=None, help='Language ID.')
+    @click.option('--sample', '-s', is_flag=True, help='Enable sampling instead of argmax')
+    @click.option('--top-k', '-tk', type=int, default=0, help='Top-K sampling (range: 1-20)')
+    @click.option('--top-p', '-tp', type=float, default=0.0, help='Top-P sampling (range: 0.1-1)')
+    @click.option('--temperature', '-temp', type=float, default=1.0, help='Sampling temperature (range: 0.1-2)')
+    @click.option('--device', '-d', type=str, default="auto", help='Device to use: "cuda" or "cuda:0".')
+    @click.option('--confidence-threshold', '-ct', type=float, default=None,
+                  help='Suppress predictions with low confidence. Set 0 to disable.')
+    def main(path, checkpoint, config, output, lang_id, sample, top_k, top_p, temperature, device, confidence_threshold):
+        if sample:  # same validation and messages as REF/infer.py:377-392
+            if top_k <= 0 and top_p <= 0.0:
+                print("Sampling is enabled but neither --top-k nor --top-p is set.")
+                sys.exit(1)
+            if top_k > 0 and top_p > 0.0:
+                print("You can't use both --top-k and --top-p at the same time.")
+                sys.exit(1)
+            if top_k < 0:
+                print("top-k must be ≥ 1.")
+                sys.exit(1)
+            if top_p < 0.0 or top_p > 1.0:
+                print("top-p must be between 0.1 and 1.0.")
+                sys.exit(1)
+            if temperature <= 0.0:
+                print("temperature must be greater than 0.")
+                sys.exit(1)
+        requested = device.lower()
+        if requested == "auto":
+            device = "cuda"
+        if not torch.cuda.is_available() or not device.startswith("cuda"):
+            print("wfl_asr_b200 needs a CUDA device (B200, sm_100a); there is no CPU path.", file=sys.stderr)
+            sys.exit(1)
+        inf_path = Path(path)
+        cfg = load_config(Path(config))
+        if confidence_threshold is None:
+            confidence_threshold = cfg["postprocess"].get("confidence_threshold", 0.0)
+        output_path = inf_path if output == "." else output
+        if not inf_path.exists():
+            print(f"Unable to locate folder {str(inf_path)}")
+            sys.exit(1)
+        if lang_id is not None and lang_id <= -1:
+            lang_id = None
+        kw = dict(config_path=str(config), checkpoint_path=str(checkpoint), device=device, lang_id=lang_id,
+                  sample=sample, top_k=top_k, top_p=top_p, temperature=temperature,
+                  confidence_threshold=confidence_threshold)
+        if inf_path.is_dir():
+            infer_folder(folder_path=str(inf_path), output_dir=str(output_path), **kw)
+        else:
+            segments = infer_audio(audio_path=str(inf_path), output_lab_path=str(output_path), **kw)
+            print("Predicted segments:")
+            for start, end, ph in segments:
+                print(f"({round(start, 2)}, {round(end, 2)}, {ph})")
+
+    main()
+
+
+if __name__ == "__main__":
+    _cli()

@@ -1,0 +1,160 @@
+"""Thin torch-tensor wrappers over the C ABI (include/wfl_b200.h).  Torch is used for device memory and
+the current stream only; every op below is one or more launches of the hand-written sm_100a kernels.
+All wrappers require CUDA tensors and raise ``WflError`` otherwise -- there is no CPU path."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, MERGE_MODES, OUT_ADD_F32, OUT_GLU_BF16, OUT_STORE_BF16,  # noqa: F401
+                   OUT_STORE_F32, GemmDesc, Segment, WflError)
+
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+TIMING = None  # bench.py sets this to a list: every GEMM launch appends (tag, algorithmic flops, start, end events)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise WflError("wfl ops need CUDA tensors (no CPU fallback exists)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_stride, a_batch_stride=0, batches=1,
+         m_rows=None, out_row_stride=None, out_batch_stride=0, bias=None, bias_batch_stride=0, act=ACT_NONE,
+         out_mode=OUT_STORE_BF16, alpha=1.0, tile_n=0):
+    """acc[b,t,n] = sum_s sum_k A[b, t+shift_s, col_s+k] * W[n, s*slab_k+k]; see wfl_gemm in the header."""
+    d = GemmDesc()
+    d.a = a.data_ptr()
+    d.a_rows, d.a_cols, d.a_row_stride, d.a_batch_stride, d.batches = a_rows, a_cols, a_row_stride, a_batch_stride, batches
+    d.w = w.data_ptr()
+    d.n, d.slab_k, d.num_slabs = n, slab_k, len(shifts)
+    for i, (s, c) in enumerate(zip(shifts, cols)):
+        d.slab_row_shift[i] = s
+        d.slab_a_col[i] = c
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.bias_batch_stride = bias_batch_stride
+    d.act, d.out_mode, d.alpha = act, out_mode, alpha
+    d.out = out.data_ptr()
+    d.m_rows = a_rows if m_rows is None else m_rows
+    out_cols = n // 2 if out_mode == OUT_GLU_BF16 else n
+    d.out_row_stride = out_cols if out_row_stride is None else out_row_stride
+    d.out_batch_stride = out_batch_stride
+    d.tile_n = tile_n
+    if not (a.is_cuda and w.is_cuda and out.is_cuda):
+        raise WflError("wfl_gemm needs CUDA tensors (no CPU fallback exists)")
+    if TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(_lib.load().wfl_gemm(ctypes.byref(d), _stream()), "wfl_gemm")
+    if TIMING is not None:
+        e1.record()
+        tag = f"M{batches * d.m_rows}xN{n}xK{len(shifts) * slab_k}/slabs{len(shifts)}/mode{out_mode}"
+        TIMING.append((tag, 2.0 * batches * d.m_rows * n * len(shifts) * slab_k, e0, e1))
+    _count()
+
+
+def linear(a2d, w, out2d, **kw):
+    """a2d [M, K] bf16 (contiguous rows), w [N, K] bf16 -> out2d [M, N or N/2]."""
+    M, K = a2d.shape
+    gemm(a2d, w, out2d, n=w.shape[0], slab_k=K, a_rows=M, a_cols=K, a_row_stride=a2d.stride(0), m_rows=M,
+         out_row_stride=out2d.stride(0), **kw)
+
+
+def attention(qkv, out, *, B, T, H, hd, scale, q_col, k_col, v_col, rel_bias=None, gate=None):
+    """qkv bf16 [B, T, W]; out bf16 [B, T, H*hd]."""
+    rc = _lib.load().wfl_attention(_ptr(qkv), qkv.stride(1), qkv.stride(0), q_col, k_col, v_col, B, T, H, hd, scale,
+                                   _ptr(rel_bias), _ptr(gate), _ptr(out), out.stride(1), out.stride(0), _stream())
+    _lib.check(rc, "wfl_attention")
+    _count()
+
+
+def layernorm(x, gamma, beta, *, out_f32=None, out_bf16=None, gamma2=None, beta2=None, eps=1e-5):
+    rows = x.numel() // x.shape[-1]
+    rc = _lib.load().wfl_layernorm(_ptr(x), rows, x.shape[-1], _ptr(gamma), _ptr(beta), _ptr(gamma2), _ptr(beta2), eps,
+                                   _ptr(out_f32), _ptr(out_bf16), _stream())
+    _lib.check(rc, "wfl_layernorm")
+    _count()
+
+
+def split_bf16(x, out):
+    rows = x.numel() // x.shape[-1]
+    _lib.check(_lib.load().wfl_split_bf16(_ptr(x), rows, x.shape[-1], _ptr(out), _stream()), "wfl_split_bf16")
+    _count()
+
+
+def broadcast_rows(src, dst, batches):
+    rows, d = src.shape
+    _lib.check(_lib.load().wfl_broadcast_rows(_ptr(src), rows, d, batches, _ptr(dst), _stream()), "wfl_broadcast_rows")
+    _count()
+
+
+def rowdot_sigmoid(x_bf16, w, b, out):
+    rows = x_bf16.numel() // x_bf16.shape[-1]
+    rc = _lib.load().wfl_rowdot_sigmoid(_ptr(x_bf16), rows, x_bf16.shape[-1], _ptr(w), _ptr(b), w.shape[0], _ptr(out),
+                                        _stream())
+    _lib.check(rc, "wfl_rowdot_sigmoid")
+    _count()
+
+
+def peak_normalize(samples_f64, clip_begin, n_clips, out, scratch_max, out_f64=None):
+    rc = _lib.load().wfl_peak_normalize(_ptr(samples_f64), _ptr(clip_begin), n_clips, _ptr(out),
+                                        out.stride(0) if out is not None else 0, _ptr(out_f64), _ptr(scratch_max),
+                                        _stream())
+    _lib.check(rc, "wfl_peak_normalize")
+    _count(2)
+
+
+def whisper_logmel(wave, n_samples, basis, filters, n_mels, out, scratch_logspec, scratch_max):
+    B = wave.shape[0]
+    rc = _lib.load().wfl_whisper_logmel(_ptr(wave), wave.stride(0), n_samples, B, _ptr(basis), _ptr(filters), n_mels,
+                                        _ptr(out), out.shape[-1], _ptr(scratch_logspec), _ptr(scratch_max), _stream())
+    _lib.check(rc, "wfl_whisper_logmel")
+    _count(2)
+
+
+def decode_frames(logits2d, L, o_id, threshold, ids):
+    rows = logits2d.shape[0]
+    rc = _lib.load().wfl_decode_frames(_ptr(logits2d), rows, L, logits2d.stride(0), o_id, threshold, _ptr(ids), _stream())
+    _lib.check(rc, "wfl_decode_frames")
+    _count()
+
+
+def median_filter(ids_in, ids_out, lengths, k):
+    n_clips, stride = ids_in.shape
+    rc = _lib.load().wfl_median_filter(_ptr(ids_in), _ptr(ids_out), _ptr(lengths), n_clips, stride, k, _stream())
+    _lib.check(rc, "wfl_median_filter")
+    _count()
+
+
+def bio_decode(ids, offsets, lengths, label_kind, label_ph, frame_duration, time_shift, segs, nseg):
+    n_clips, stride = ids.shape
+    rc = _lib.load().wfl_bio_decode(_ptr(ids), _ptr(offsets), _ptr(lengths), n_clips, stride, _ptr(label_kind),
+                                    _ptr(label_ph), label_kind.numel(), frame_duration, _ptr(time_shift), _ptr(segs),
+                                    _ptr(nseg), _stream())
+    _lib.check(rc, "wfl_bio_decode")
+    _count()
+
+
+def merge_segments(segs, nseg, clip_stride, file_clip_begin, n_files, ph_class, mode, out, nout):
+    if mode not in MERGE_MODES:
+        raise ValueError(f"Unsupported merge mode: {mode}")  # REF/utils.py:185
+    rc = _lib.load().wfl_merge_segments(_ptr(segs), _ptr(nseg), clip_stride, _ptr(file_clip_begin), n_files,
+                                        _ptr(ph_class), MERGE_MODES[mode], _ptr(out), _ptr(nout), _stream())
+    _lib.check(rc, "wfl_merge_segments")
+    _count()
+
+
+def htk_times(segs, n, start_out, end_out):
+    _lib.check(_lib.load().wfl_htk_times(_ptr(segs), n, _ptr(start_out), _ptr(end_out), _stream()), "wfl_htk_times")
+    _count()

@@ -1,0 +1,66 @@
+"""Weight packing: reference ``state_dict`` tensors (fp32, reference layouts) -> the bf16 layouts the
+sm_100a kernels consume.  Pure tensor reshuffles and folds, done once at load time:
+
+* Conv1d [out, in, k] -> [out][tap][in] so each tap is one K-slab of the implicit GEMM
+* eval-mode BatchNorm1d folded into the preceding conv (REF/model.py:33-34)
+* GLU value/gate rows interleaved per output tile (REF/model.py:31-32)
+* lang_proj split into W_h and a per-language bias  W_e @ emb[l] + b  (REF/model.py:176-180)
+* q/k/v projections concatenated (Whisper k_proj has no bias -> zeros)
+* hi/lo bf16 split of precision-critical tail weights (classifier)
+"""
+import torch
+
+
+def bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def conv_taps(weight):
+    """[out, in, k] -> [out, k*in] with tap-major K (tap j multiplies input row t + j*dil - pad)."""
+    o, i, k = weight.shape
+    return weight.permute(0, 2, 1).reshape(o, k * i).contiguous()
+
+
+def pad_k(weight2d, k_to):
+    o, k = weight2d.shape
+    if k == k_to:
+        return weight2d
+    out = weight2d.new_zeros(o, k_to)
+    out[:, :k] = weight2d
+    return out
+
+
+def fold_batchnorm(conv_w, conv_b, gamma, beta, mean, var, eps=1e-5):
+    """y = BN(conv(x)) == conv'(x): w' = w * g/sqrt(var+eps), b' = (b - mean) * g/sqrt(var+eps) + beta."""
+    s = gamma / torch.sqrt(var + eps)
+    return conv_w * s[:, None, None], (conv_b - mean) * s + beta
+
+
+def interleave_glu(weight2d, bias, tile_n):
+    """Rows [0,d) are GLU values, [d,2d) gates.  Reorder so each block of tile_n rows holds tile_n/2 values
+    followed by their tile_n/2 gates -- the layout WFL_OUT_GLU_BF16 expects."""
+    two_d = weight2d.shape[0]
+    d = two_d // 2
+    h = tile_n // 2
+    assert d % h == 0, "GLU width must be a multiple of tile_n/2"
+    idx = []
+    for t in range(d // h):
+        idx += list(range(t * h, (t + 1) * h)) + list(range(d + t * h, d + (t + 1) * h))
+    idx = torch.tensor(idx, device=weight2d.device)
+    return weight2d[idx].contiguous(), (bias[idx].contiguous() if bias is not None else None)
+
+
+def split_hi_lo(weight2d):
+    """fp32 [n, k] -> bf16 [n, 3k] = [hi | hi | lo]: pairs with A = [hi | lo] slabs (cols 0, k, 0)."""
+    hi = weight2d.to(torch.bfloat16)
+    lo = (weight2d - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
+
+
+def pad_rows(weight2d, rows_to):
+    n, k = weight2d.shape
+    if n == rows_to:
+        return weight2d
+    out = weight2d.new_zeros(rows_to, k)
+    out[:n] = weight2d
+    return out

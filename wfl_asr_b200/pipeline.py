@@ -1,0 +1,130 @@
+"""Batched labeling pipeline: waveforms -> forward -> threshold/argmax -> median -> BIO runs -> merged
+segments, with every per-frame result staying on the device (one D2H copy of the final segment records).
+
+It is the batched equivalent of the per-file body of REF/infer.py:251-310 (single chunk) and
+REF/infer.py:98-184 (30 s chunks of long files: per-chunk decode, time shift, merge across chunks).
+"""
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import TAG_B, TAG_I, TAG_O, TAG_OTHER
+
+SEG_DTYPE = np.dtype([("start", "<f8"), ("end", "<f8"), ("ph", "<i4"), ("pad", "<i4")])
+FRAME_DURATION = 0.02  # REF/infer.py:12
+
+
+def label_tables(labels):
+    """Label strings -> (phoneme names, kind[int8], ph[int32]) as REF/utils.py:10-61 classifies tags."""
+    phon, index, kind, ph = [], {}, [], []
+    for t in labels:
+        if t == "O":
+            kind.append(TAG_O)
+            ph.append(-1)
+        elif t.startswith("B-") or t.startswith("I-"):
+            name = t[2:]
+            if name not in index:
+                index[name] = len(phon)
+                phon.append(name)
+            kind.append(TAG_B if t.startswith("B-") else TAG_I)
+            ph.append(index[name])
+        else:
+            kind.append(TAG_OTHER)
+            ph.append(-1)
+    return phon, kind, ph
+
+
+class Labeler:
+    def __init__(self, model, median_filter=1, merge_mode="right", confidence_threshold=0.0, ph_names_out=None):
+        """``ph_names_out``: optional list mapping phoneme index -> output name (the canonical_to_lang remap of
+        REF/infer.py:303-307); equal output names merge as equal labels (REF/utils.py:148-186)."""
+        if merge_mode not in ops.MERGE_MODES:
+            raise ValueError(f"Unsupported merge mode: {merge_mode}")
+        self.model = model
+        self.dev = next(model.parameters()).device
+        self.labels = list(model.label_list)
+        if "O" not in model.label2id:
+            raise KeyError("label list has no 'O' tag")  # REF/infer.py:297 indexes label2id["O"]
+        self.o_id = model.label2id["O"]
+        self.median = int(median_filter)
+        self.merge_mode = merge_mode
+        self.threshold = float(confidence_threshold)
+        self.phon, kind, ph = label_tables(self.labels)
+        self.kind = torch.tensor(kind, dtype=torch.int8, device=self.dev)
+        self.ph = torch.tensor(ph, dtype=torch.int32, device=self.dev)
+        self.set_output_names(ph_names_out)
+        self._ws = {}
+
+    def set_output_names(self, names):
+        self.out_names = list(names) if names is not None else list(self.phon)
+        if names is None:
+            self.ph_class = None
+        else:
+            cls, seen = [], {}
+            for n in self.out_names:
+                cls.append(seen.setdefault(n, len(seen)))
+            self.ph_class = torch.tensor(cls, dtype=torch.int32, device=self.dev)
+
+    def _buffers(self, n_clips, stride):
+        key = (n_clips, stride)
+        ws = self._ws.get(key)
+        if ws is None:
+            dev = self.dev
+            ws = {
+                "ids": torch.empty(n_clips, stride, dtype=torch.int32, device=dev),
+                "ids2": torch.empty(n_clips, stride, dtype=torch.int32, device=dev),
+                "segs": torch.empty(n_clips, stride, 24, dtype=torch.uint8, device=dev),
+                "merged": torch.empty(n_clips, stride, 24, dtype=torch.uint8, device=dev),
+                "nseg": torch.empty(n_clips, dtype=torch.int32, device=dev),
+                "nout": torch.empty(n_clips, dtype=torch.int32, device=dev),
+            }
+            self._ws = {key: ws}
+        return ws
+
+    @torch.no_grad()
+    def postprocess(self, logits, offsets, lengths=None, file_clip_begin=None, time_shift=None):
+        """logits [B,T,L] fp32, offsets [B,T,2] fp32 (device) -> (merged segs [B,T] records, nout [n_files]).
+        Launches: decode_frames, median_filter (if size > 1), bio_decode, merge_segments."""
+        B, T, L = logits.shape
+        ws = self._buffers(B, T)
+        if lengths is None:
+            lengths = torch.full((B,), T, dtype=torch.int32, device=self.dev)
+        n_files = B if file_clip_begin is None else file_clip_begin.numel() - 1
+        if file_clip_begin is None:
+            file_clip_begin = torch.arange(B + 1, dtype=torch.int32, device=self.dev)
+        lg2 = logits.reshape(B * T, L) if logits.is_contiguous() else logits.as_strided((B * T, L), (logits.stride(1), 1))
+        ops.decode_frames(lg2, L, self.o_id, self.threshold, ws["ids"])
+        ids = ws["ids"]
+        if self.median > 1:
+            ops.median_filter(ws["ids"], ws["ids2"], lengths, self.median)
+            ids = ws["ids2"]
+        ops.bio_decode(ids, offsets, lengths, self.kind, self.ph, FRAME_DURATION, time_shift, ws["segs"], ws["nseg"])
+        ops.merge_segments(ws["segs"], ws["nseg"], T, file_clip_begin, n_files, self.ph_class, self.merge_mode,
+                           ws["merged"], ws["nout"])
+        return ids, ws["merged"], ws["nout"], file_clip_begin, n_files
+
+    @torch.no_grad()
+    def label(self, wave, lang_id=None, file_clip_begin=None, time_shift=None):
+        """wave [B, N] fp32 on the device -> list (per file) of [(start, end, phoneme)] python tuples."""
+        logits, offsets = self.model(wave, lang_id)
+        _, merged, nout, fcb, n_files = self.postprocess(logits, offsets, None, file_clip_begin, time_shift)
+        return self.fetch(merged, nout, fcb, n_files, logits.shape[1])
+
+    @torch.no_grad()
+    def label_host(self, wave_host, lang_id=None):
+        """End-to-end call with HOST buffers: (pinned) fp32 [B, N] -> H2D -> label -> D2H -> python segments."""
+        wave = wave_host.to(self.dev, non_blocking=True)
+        return self.label(wave, lang_id)
+
+    def fetch(self, merged, nout, file_clip_begin, n_files, stride):
+        """One D2H copy of the segment records (+ counts); returns python tuples like the reference."""
+        counts = nout[:n_files].cpu().numpy()
+        begins = file_clip_begin.cpu().numpy()
+        raw = merged.cpu().numpy().reshape(-1).view(SEG_DTYPE)
+        out = []
+        for f in range(n_files):
+            base = int(begins[f]) * stride
+            rec = raw[base:base + int(counts[f])]
+            names = self.out_names
+            out.append([(float(s), float(e), names[int(p)]) for s, e, p in zip(rec["start"], rec["end"], rec["ph"])])
+        return out
