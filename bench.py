@@ -91,8 +91,7 @@ def run_ours(args, rank, world, local_rank):
     batch = args.batch or wl["batch"]
     cfg = synth.workload_config(WORKLOAD)
     labels = synth.synth_labels(30)
-    torch.manual_seed(0)
-    model = synth.randomize_batchnorm(BIOPhonemeTagger(cfg, labels)).to(dev).eval()
+    model = synth.bench_model(BIOPhonemeTagger, cfg, labels).to(dev).eval()
     pp = cfg["postprocess"]
     labeler = Labeler(model, median_filter=pp["median_filter"], merge_mode=pp["merge_segments"],
                       confidence_threshold=pp["confidence_threshold"])
@@ -199,8 +198,7 @@ def cpu_reference_run(steps, warmup, sample_clips, seconds):
     from wfl_asr_b200.model import BIOPhonemeTagger
     cfg = synth.workload_config(WORKLOAD)
     labels = synth.synth_labels(30)
-    torch.manual_seed(0)
-    model = synth.randomize_batchnorm(BIOPhonemeTagger(cfg, labels))
+    model = synth.bench_model(BIOPhonemeTagger, cfg, labels)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     torch.set_num_threads(os.cpu_count() or 1)
     wave = torch.from_numpy(np.stack([synth.synth_wave(i, seconds) for i in range(sample_clips)]).astype(np.float32))

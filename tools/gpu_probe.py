@@ -39,6 +39,10 @@ def main():
         line = f"{status:10s} {fn}  ({time.time() - t:.1f}s)"
         print(line, flush=True)
         report.write(line + "\n")
+        info = [l for l in out.splitlines() if l.startswith("[")]
+        if rc == 0 and info:
+            print("\n".join(info[:20]), flush=True)
+            report.write("\n".join(info[:20]) + "\n")
         if rc != 0:
             tail = "\n".join(out.splitlines()[-60:])
             keep = [l for l in out.splitlines() if l.startswith("[") or "Error" in l or "error" in l or "assert" in l or "wfl:" in l]

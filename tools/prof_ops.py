@@ -1,0 +1,48 @@
+"""Runs single ops at bench shapes (for ncu captures): python tools/prof_ops.py attn64 attn256 ln logmel gemm"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from wfl_asr_b200 import ops
+from wfl_asr_b200.frontend import whisper_frontend_constants
+dev = torch.device("cuda:0")
+B, T, d = 32, 1500, 512
+which = sys.argv[1:] or ["attn64"]
+reps = int(os.environ.get("REPS", "2"))
+g = torch.Generator().manual_seed(0)
+def t_ms(fn):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+for w in which:
+    if w.startswith("attn"):
+        hd = int(w[4:]); H = d // hd if hd <= 256 else 2
+        dd = H * hd
+        qkv = (torch.randn(B, T, 3 * dd, generator=g) * 0.5).to(dev).bfloat16()
+        out = torch.empty(B, T, dd, device=dev, dtype=torch.bfloat16)
+        ms = t_ms(lambda: ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=hd ** -0.5, q_col=0, k_col=dd, v_col=2 * dd))
+        print(f"{w}: {ms:.3f} ms  {4.0 * T * T * dd * B / ms / 1e9:.1f} TFLOP/s")
+    elif w == "ln":
+        x = torch.randn(B * T, d, generator=g).to(dev); gm = torch.ones(d, device=dev); bt = torch.zeros(d, device=dev)
+        o = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
+        ms = t_ms(lambda: ops.layernorm(x, gm, bt, out_bf16=o))
+        print(f"ln: {ms:.4f} ms  {B * T * d * 6 / ms / 1e6:.0f} GB/s")
+    elif w == "logmel":
+        wave = (torch.randn(B, 480000, generator=g) * 0.1).to(dev)
+        basis, filt = whisper_frontend_constants(80, dev)
+        out = torch.empty(B, 3000, 128, device=dev, dtype=torch.bfloat16)
+        s1 = torch.empty(B, 3000, 80, device=dev); s2 = torch.empty(B, device=dev)
+        ms = t_ms(lambda: ops.whisper_logmel(wave, 480000, basis, filt, 80, out, s1, s2))
+        print(f"logmel: {ms:.3f} ms")
+    elif w.startswith("gemm"):
+        # gemmN_K[_mode]
+        parts = w[4:].split("_"); N, K = int(parts[0]), int(parts[1]); mode = int(parts[2]) if len(parts) > 2 else 0
+        tile = int(parts[3]) if len(parts) > 3 else 0
+        a = torch.randn(B * T, K, generator=g).to(dev).bfloat16(); wt = (torch.randn(N, K, generator=g) * K ** -0.5).to(dev).bfloat16()
+        o = torch.zeros(B * T, N, device=dev, dtype=torch.float32 if mode in (1, 2) else torch.bfloat16)
+        bias = torch.zeros(N, device=dev)
+        ms = t_ms(lambda: ops.linear(a, wt, o, bias=bias, out_mode=mode, act=ops.ACT_GELU if mode == 0 else 0, tile_n=tile))
+        print(f"{w}: {ms:.4f} ms  {2.0 * B * T * N * K / ms / 1e9:.1f} TFLOP/s")

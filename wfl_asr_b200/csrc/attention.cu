@@ -15,6 +15,8 @@
 // Reference arithmetic replaced: TF/models/whisper/modeling_whisper.py:284-357 (SDPA, q pre-scaled),
 // nn.MultiheadAttention at REF/model.py:26,42 (TORCH/nn/functional.py multi_head_attention_forward),
 // TF/models/wavlm/modeling_wavlm.py:147-241 (additive gated relative position bias).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace wfl {
@@ -22,6 +24,12 @@ namespace wfl {
 constexpr int kAttnThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int HD, int KV_TILE, int KV_STAGES>
 struct AttnCfg {
@@ -35,6 +43,8 @@ struct AttnCfg {
   static constexpr int kSmemBytes = kQBytes + KV_STAGES * kStageBytes + 2 * kPBytes + 256 + 1024;
   static constexpr int kOCol = 2 * KV_TILE;  // TMEM column where O starts (after two S buffers)
   static_assert(kOCol + HD <= 512, "TMEM overflow");
+  static constexpr uint32_t kTmemCols = kOCol + HD <= 256 ? 256 : 512;
+  static constexpr int kCtasPerSm = (kSmemBytes <= 113 * 1024 && kTmemCols <= 256) ? 2 : 1;
 };
 
 struct AttnParams {
@@ -46,7 +56,7 @@ struct AttnParams {
 };
 
 template <int HD, int KV_TILE, int KV_STAGES>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_TILE, KV_STAGES>::kCtasPerSm))
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                  const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
   using Cfg = AttnCfg<HD, KV_TILE, KV_STAGES>;
@@ -91,7 +101,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -205,76 +215,102 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       tc_fence_after();
       const uint32_t s_addr = lane_addr + sb * KV_TILE;
 
-      // pass 1: row max of the scaled scores
-      float m_tile = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < KV_TILE; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = kv0 + c + i;
-          float x = __uint_as_float(v[i]) * p.scale_log2;
-          if (has_bias && k < p.T) x = fmaf(gate_l2, __ldg(bias_row + k), x);
-          x = k < p.T ? x : -INFINITY;
-          m_tile = fmaxf(m_tile, x);
-        }
-      }
-      float m_new = fmaxf(m_used, m_tile);
-      const bool grow = m_new > m_used + kRescaleThreshold;  // also true on the first tile (m_used = -inf)
-      if (__any_sync(0xffffffffu, grow)) {
-        if (j > 0) {
-          // O holds sum_{i<j} P_i V_i scaled by 2^-m_used: rescale it (all rows of this warp) once PV(j-1) retired
-          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          tc_fence_after();
-          const float factor = exp2f(m_used - m_new);
-#pragma unroll 1
-          for (int c = 0; c < HD; c += 32) {
-            uint32_t o[32];
-            tmem_ld32(lane_addr + Cfg::kOCol + c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st32(lane_addr + Cfg::kOCol + c, o);
+      // One tile of online softmax, specialised on (relative-position bias, partial last tile) so the common
+      // case costs ~1 FMNMX (pass 1) and FFMA + MUFU.EX2 + FADD + half a CVT (pass 2) per score.
+      auto tile = [&](auto bias_c, auto tail_c) {
+        constexpr bool kBias = decltype(bias_c)::value;
+        constexpr bool kTail = decltype(tail_c)::value;
+        // x(v, k): score in log2 units
+        auto score = [&](uint32_t raw, int k) -> float {
+          float x = __uint_as_float(raw) * p.scale_log2;
+          if constexpr (kBias) {
+            if (!kTail || k < p.T) x = fmaf(gate_l2, __ldg(bias_row + k), x);
           }
-          tmem_st_wait();
-          l_sum *= factor;
+          if constexpr (kTail) x = k < p.T ? x : -INFINITY;
+          return x;
+        };
+        // pass 1: row max
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < KV_TILE; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(s_addr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if constexpr (!kBias && !kTail)
+              mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(v[i]));  // scale > 0: max commutes with the scaling
+            else
+              mx[i & 3] = fmaxf(mx[i & 3], score(v[i], kv0 + c + i));
+          }
         }
-        m_used = m_new;
-      }
+        float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if constexpr (!kBias && !kTail) m_tile *= p.scale_log2;
+        const float m_new = fmaxf(m_used, m_tile);
+        const bool grow = m_new > m_used + kRescaleThreshold;  // also true on the first tile (m_used = -inf)
+        if (__any_sync(0xffffffffu, grow)) {
+          if (j > 0) {
+            // O holds sum_{i<j} P_i V_i scaled by 2^-m_used: rescale it (all rows of this warp) once PV(j-1) retired
+            mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            tc_fence_after();
+            const float factor = ex2_approx(m_used - m_new);
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(lane_addr + Cfg::kOCol + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st32(lane_addr + Cfg::kOCol + c, o);
+            }
+            tmem_st_wait();
+            l_sum *= factor;
+          }
+          m_used = m_new;
+        }
+        // the P buffer we are about to overwrite was read by PV(j-2)
+        if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
 
-      // the P buffer we are about to overwrite was read by PV(j-2)
-      if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
-
-      // pass 2: P = 2^(x - m_used) -> bf16 -> swizzled smem; row sum in fp32
-      uint8_t* p_row = p_smem + sb * Cfg::kPBytes + r * 128;
+        // pass 2: P = 2^(x - m_used) -> bf16 -> swizzled smem; row sum in fp32
+        uint8_t* p_row = p_smem + sb * Cfg::kPBytes + r * 128;
+        const float neg_m = -m_used;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < KV_TILE; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c, v);
-        tmem_ld_wait();
-        float pf[32];
+        for (int c = 0; c < KV_TILE; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(s_addr + c, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = kv0 + c + i;
-          float x = __uint_as_float(v[i]) * p.scale_log2;
-          if (has_bias && k < p.T) x = fmaf(gate_l2, __ldg(bias_row + k), x);
-          const float e = k < p.T ? exp2f(x - m_used) : 0.f;
-          pf[i] = e;
-          l_sum += e;
+          for (int i = 0; i < 32; i += 2) {
+            float e0, e1;
+            if constexpr (!kBias && !kTail) {
+              e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+              e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
+            } else {
+              e0 = ex2_approx(score(v[i], kv0 + c + i) + neg_m);
+              e1 = ex2_approx(score(v[i + 1], kv0 + c + i + 1) + neg_m);
+            }
+            sum[(i >> 1) & 3] += e0 + e1;
+            pk[i >> 1] = pack_bf16(e0, e1);
+          }
+          uint8_t* blk = p_row + (c >> 6) * (128 * 128);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk16 = ((c & 63) >> 3) + q4;
+            *reinterpret_cast<uint4*>(blk + ((chunk16 ^ (r & 7)) << 4)) =
+                make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
         }
-        uint8_t* blk = p_row + (c >> 6) * (128 * 128);
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 u;
-          u.x = pack_bf16(pf[8 * q4 + 0], pf[8 * q4 + 1]);
-          u.y = pack_bf16(pf[8 * q4 + 2], pf[8 * q4 + 3]);
-          u.z = pack_bf16(pf[8 * q4 + 4], pf[8 * q4 + 5]);
-          u.w = pack_bf16(pf[8 * q4 + 6], pf[8 * q4 + 7]);
-          const int chunk16 = ((c & 63) >> 3) + q4;
-          *reinterpret_cast<uint4*>(blk + ((chunk16 ^ (r & 7)) << 4)) = u;
-        }
+        l_sum += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+      };
+      const bool tail = kv0 + KV_TILE > p.T;  // warp-uniform
+      if (has_bias) {
+        if (tail) tile(std::true_type{}, std::true_type{});
+        else tile(std::true_type{}, std::false_type{});
+      } else {
+        if (tail) tile(std::false_type{}, std::true_type{});
+        else tile(std::false_type{}, std::false_type{});
       }
       // S buffer consumed; P visible to the tensor core (async proxy)
       tc_fence_before();
@@ -321,7 +357,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -391,7 +427,7 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
   p.gate = gate;
   switch (hd) {
     case 64:
-      return launch_attention<64, 128, 3>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+      return launch_attention<64, 64, 3>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                           out_batch_stride, stream);
     case 256:
       return launch_attention<256, 64, 2>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,

@@ -57,22 +57,22 @@ struct GemmParams {
 // erf(|x|) = 1 - 2^q(|x|) with q a degree-8 polynomial fitted to log2(erfc) on [0, 4.3] (coefficients from
 // tools/fit_erf.py; max abs error of the resulting erf 2.4e-7 in fp32) -- one MUFU.EX2 per element instead of
 // libdevice erff's branches, so the GELU epilogue keeps pace with the tensor pipe.
-__device__ __forceinline__ float fast_erf(float x) {
-  float t = fminf(fabsf(x), 4.3f);
-  float q = WFL_ERF_C8;
-  q = fmaf(q, t, WFL_ERF_C7);
-  q = fmaf(q, t, WFL_ERF_C6);
-  q = fmaf(q, t, WFL_ERF_C5);
+// gelu(v) = v * Phi(v) with Phi(-|v|) = 0.5 erfc(|v|/sqrt2) = 2^(t P(t) - 1), t = min(|v|/sqrt2, 4.3):
+// 6 FMA-pipe ops + one MUFU.EX2, then a sign select.  |error| < 2e-6, far below the bf16 rounding of the result.
+__device__ __forceinline__ float fast_gelu(float v) {
+  const float t = fminf(fabsf(v) * 0.70710678118654752f, 4.3f);
+  float q = WFL_ERF_C5;
   q = fmaf(q, t, WFL_ERF_C4);
   q = fmaf(q, t, WFL_ERF_C3);
   q = fmaf(q, t, WFL_ERF_C2);
   q = fmaf(q, t, WFL_ERF_C1);
-  q = q * t;
-  float r = 1.0f - exp2f(q);
-  return copysignf(r, x);
+  q = fmaf(q, t, -1.0f);
+  float h;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(q));
+  return v * (v >= 0.0f ? 1.0f - h : h);
 }
 __device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == WFL_ACT_GELU) return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752f));
+  if (act == WFL_ACT_GELU) return fast_gelu(v);
   if (act == WFL_ACT_RELU) return fmaxf(v, 0.0f);
   return v;
 }
@@ -240,11 +240,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
         } else {
           tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(bsm + col);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = apply_act(__uint_as_float(v[i]) + bsm[col + i], p.act);
-            if constexpr (OUT_MODE == WFL_OUT_ADD_F32) a *= p.alpha;
-            f[i] = a;
+          for (int i = 0; i < 8; ++i) {
+            const float4 bv = b4[i];
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bv.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bv.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bv.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bv.w;
+          }
+          if (p.act == WFL_ACT_GELU) {  // warp-uniform: keep the activation choice out of the element loop
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fast_gelu(f[i]);
+          } else if (p.act == WFL_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+          }
+          if constexpr (OUT_MODE == WFL_OUT_ADD_F32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] *= p.alpha;
           }
         }
         if constexpr (kF32) {

@@ -1,0 +1,238 @@
+// K11 -- bidirectional LSTM recurrence as a persistent thread-block-cluster kernel (no cuDNN-RNN).
+//
+// Reference: nn.LSTM(batch_first, bidirectional) at REF/model.py:105-111,183 (gates i,f,g,o; h0=c0=0;
+// layer l>0 consumes [fwd | bwd] of layer l-1).  The input projection x W_ih^T + b_ih + b_hh is one dense
+// GEMM (gemm.cu) for all time steps; this kernel runs the T strictly serial steps
+//     a_t = gx_t + W_hh h_{t-1};  c_t = s(f) c_{t-1} + s(i) tanh(g);  h_t = s(o) tanh(c_t)
+// One cluster of 8 CTAs owns one direction for a group of 8 batch items:
+//   * W_hh (bf16) never leaves the register file: CTA r holds the 4 gate rows of hidden units
+//     [r*H/8, (r+1)*H/8) as mma.sync m16n8k16 A-fragments, split over (unit group) x (K half) warps.
+//     Row tiles are arranged (i|f) and (g|o) per 8 units, so one thread ends up with all four gate
+//     pre-activations of its (unit, batch) cells and the cell update needs no data exchange.
+//   * h_{t-1} (bf16, [batch][H]) lives in shared memory of every CTA, double buffered; after the cell
+//     update each CTA pushes its H/8 slice to all 8 CTAs with 16-byte DSMEM stores and the cluster
+//     meets at one barrier.cluster per step.  c_t stays in fp32 registers for the whole sequence.
+//   * gx_t is prefetched one step ahead as float4 (columns are packed [dir][unit][gate]).
+// The recurrence is latency-bound (T serial steps), not FLOP-bound: report steps/s, not a roofline fraction.
+#include "common.cuh"
+
+namespace wfl {
+
+constexpr int kLstmCluster = 8;
+constexpr int kLstmNB = 8;  // batch items per cluster = one n8 MMA tile
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_acc(float x) {
+  // tanh(x) = 1 - 2 / (1 + e^{2x}); saturates cleanly for large |x|
+  const float e = __expf(2.0f * x);
+  return 1.0f - 2.0f / (1.0f + e);
+}
+
+template <int H>
+struct LstmCfg {
+  static constexpr int kUnits = H / kLstmCluster;   // hidden units per CTA
+  static constexpr int kGroups = kUnits / 8;        // 8-unit groups, one (pair of) warp(s) each
+  static constexpr int kKSplit = 2;
+  static constexpr int kWarps = kGroups * kKSplit;
+  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kKTiles = H / 16 / kKSplit;  // k16 tiles per warp
+  static constexpr int kHStride = H + 8;            // padded row (bank-conflict-free B fragments)
+  static constexpr int kHBufBytes = 2 * kLstmNB * kHStride * 2;
+  static constexpr int kStageBytes = kLstmNB * kUnits * 2;  // this CTA's h slice, [n][unit] bf16
+  static constexpr int kPartBytes = kGroups * 32 * 8 * 4;   // K-half partial sums
+  static constexpr int kVecPerRow = kUnits * 2 / 16;        // 16-byte vectors per (n) row of the slice
+  static_assert(H % (kLstmCluster * 8) == 0, "H must be a multiple of 64");
+  static_assert((kUnits * 2) % 16 == 0, "slice rows must be 16-byte multiples");
+};
+
+template <int H>
+__global__ void __launch_bounds__(LstmCfg<H>::kThreads, 1)
+lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh, int B, int T,
+            __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32) {
+  using Cfg = LstmCfg<H>;
+  __shared__ __align__(16) uint8_t hbuf_raw[Cfg::kHBufBytes];
+  __shared__ __align__(16) uint8_t stage_raw[Cfg::kStageBytes];
+  __shared__ __align__(16) float part[Cfg::kGroups * 32 * 8];
+  __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(hbuf_raw);  // [2][NB][kHStride]
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(stage_raw);
+
+  const int rank = blockIdx.x;  // == %cluster_ctarank (cluster spans gridDim.x)
+  const int b0 = blockIdx.y * kLstmNB;
+  const int dir = blockIdx.z;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2;   // row inside an 8-row half tile == unit inside the group == batch column for B frags
+  const int q = lane & 3;
+  const int group = warp % Cfg::kGroups;
+  const int khalf = warp / Cfg::kGroups;
+  const int unit = rank * Cfg::kUnits + group * 8 + g;  // hidden unit this thread's accumulators belong to
+
+  // ---- W_hh fragments -> registers (kept for all T steps)
+  uint32_t wa[Cfg::kKTiles][4], wb[Cfg::kKTiles][4];
+  {
+    const __nv_bfloat16* w = whh + static_cast<int64_t>(dir) * 4 * H * H;
+    const uint32_t* wi = reinterpret_cast<const uint32_t*>(w + static_cast<int64_t>(0 * H + unit) * H);
+    const uint32_t* wf = reinterpret_cast<const uint32_t*>(w + static_cast<int64_t>(1 * H + unit) * H);
+    const uint32_t* wg = reinterpret_cast<const uint32_t*>(w + static_cast<int64_t>(2 * H + unit) * H);
+    const uint32_t* wo = reinterpret_cast<const uint32_t*>(w + static_cast<int64_t>(3 * H + unit) * H);
+#pragma unroll
+    for (int kt = 0; kt < Cfg::kKTiles; ++kt) {
+      const int k = (khalf * Cfg::kKTiles + kt) * 16 + 2 * q;  // element index; /2 -> 32-bit word
+      wa[kt][0] = wi[k >> 1];
+      wa[kt][1] = wf[k >> 1];
+      wa[kt][2] = wi[(k + 8) >> 1];
+      wa[kt][3] = wf[(k + 8) >> 1];
+      wb[kt][0] = wg[k >> 1];
+      wb[kt][1] = wo[k >> 1];
+      wb[kt][2] = wg[(k + 8) >> 1];
+      wb[kt][3] = wo[(k + 8) >> 1];
+    }
+  }
+  // ---- h_0 = 0 in both buffers (pad columns included)
+  for (int i = threadIdx.x; i < Cfg::kHBufBytes / 4; i += Cfg::kThreads) reinterpret_cast<uint32_t*>(hbuf_raw)[i] = 0u;
+  cluster_sync_all();  // every CTA of the cluster is running and initialised before any DSMEM traffic
+
+  float c_state[2] = {0.f, 0.f};  // cells (unit, batch b0+2q), (unit, batch b0+2q+1); used by khalf==0 warps
+  const int bq0 = b0 + 2 * q, bq1 = b0 + 2 * q + 1;
+  const int64_t row_stride = static_cast<int64_t>(8) * H;  // gx row: [dir][unit][gate]
+  const float4* gx_base = reinterpret_cast<const float4*>(gx) + (static_cast<int64_t>(dir) * H + unit);
+  auto gx_ptr = [&](int b, int t) { return gx_base + (static_cast<int64_t>(b) * T + t) * (row_stride / 4); };
+  float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0;
+  if (khalf == 0) {
+    const int t_first = dir == 0 ? 0 : T - 1;
+    if (bq0 < B) pre0 = __ldg(gx_ptr(bq0, t_first));
+    if (bq1 < B) pre1 = __ldg(gx_ptr(bq1, t_first));
+  }
+  const uint32_t hbuf_local = smem_u32(hbuf_raw);
+
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? s : T - 1 - s;
+    const int cur = s & 1, nxt = cur ^ 1;
+    // ---- W_hh h_{t-1} for this warp's 16 gate rows x 2 tiles x 8 batch columns over its K half
+    float acc_if[4] = {0.f, 0.f, 0.f, 0.f}, acc_go[4] = {0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* hrow = hbuf + (cur * kLstmNB + g) * Cfg::kHStride + khalf * Cfg::kKTiles * 16 + 2 * q;
+#pragma unroll
+    for (int kt = 0; kt < Cfg::kKTiles; ++kt) {
+      const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16);
+      const uint32_t hb1 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16 + 8);
+      mma_bf16_16816(acc_if, wa[kt], hb0, hb1);
+      mma_bf16_16816(acc_go, wb[kt], hb0, hb1);
+    }
+    if (khalf == 1) {
+      float4* pp = reinterpret_cast<float4*>(part + (group * 32 + lane) * 8);
+      pp[0] = make_float4(acc_if[0], acc_if[1], acc_if[2], acc_if[3]);
+      pp[1] = make_float4(acc_go[0], acc_go[1], acc_go[2], acc_go[3]);
+    }
+    __syncthreads();
+    if (khalf == 0) {
+      const float4* pp = reinterpret_cast<const float4*>(part + (group * 32 + lane) * 8);
+      const float4 p_if = pp[0], p_go = pp[1];
+      // prefetch the next step's input pre-activations while this step's math runs
+      float4 nx0 = pre0, nx1 = pre1;
+      if (s + 1 < T) {
+        const int tn = dir == 0 ? s + 1 : T - 2 - s;
+        if (bq0 < B) nx0 = __ldg(gx_ptr(bq0, tn));
+        if (bq1 < B) nx1 = __ldg(gx_ptr(bq1, tn));
+      }
+      // accumulator layout: [0],[1] = first gate of the tile (rows g) for batch 2q, 2q+1; [2],[3] = second gate (rows g+8)
+      const float ai0 = acc_if[0] + p_if.x + pre0.x, ai1 = acc_if[1] + p_if.y + pre1.x;
+      const float af0 = acc_if[2] + p_if.z + pre0.y, af1 = acc_if[3] + p_if.w + pre1.y;
+      const float ag0 = acc_go[0] + p_go.x + pre0.z, ag1 = acc_go[1] + p_go.y + pre1.z;
+      const float ao0 = acc_go[2] + p_go.z + pre0.w, ao1 = acc_go[3] + p_go.w + pre1.w;
+      c_state[0] = sigmoid_acc(af0) * c_state[0] + sigmoid_acc(ai0) * tanh_acc(ag0);
+      c_state[1] = sigmoid_acc(af1) * c_state[1] + sigmoid_acc(ai1) * tanh_acc(ag1);
+      const float h0 = sigmoid_acc(ao0) * tanh_acc(c_state[0]);
+      const float h1 = sigmoid_acc(ao1) * tanh_acc(c_state[1]);
+      const int ul = group * 8 + g;  // unit inside this CTA's slice
+      stage[(2 * q) * Cfg::kUnits + ul] = __float2bfloat16_rn(h0);
+      stage[(2 * q + 1) * Cfg::kUnits + ul] = __float2bfloat16_rn(h1);
+      if (y_f32 != nullptr) {
+        if (bq0 < B) y_f32[(static_cast<int64_t>(bq0) * T + t) * (2 * H) + dir * H + unit] = h0;
+        if (bq1 < B) y_f32[(static_cast<int64_t>(bq1) * T + t) * (2 * H) + dir * H + unit] = h1;
+      }
+      pre0 = nx0;
+      pre1 = nx1;
+    }
+    __syncthreads();
+    // ---- push this CTA's slice of h_t to every CTA of the cluster (and to global as bf16)
+    constexpr int kVecs = kLstmCluster * kLstmNB * Cfg::kVecPerRow;
+    for (int i = threadIdx.x; i < kVecs; i += Cfg::kThreads) {
+      const int dst = i / (kLstmNB * Cfg::kVecPerRow);
+      const int rem = i - dst * (kLstmNB * Cfg::kVecPerRow);
+      const int n = rem / Cfg::kVecPerRow;
+      const int v = rem - n * Cfg::kVecPerRow;
+      const uint4 val = *reinterpret_cast<const uint4*>(stage_raw + (n * Cfg::kUnits) * 2 + v * 16);
+      const uint32_t off = ((nxt * kLstmNB + n) * Cfg::kHStride + rank * Cfg::kUnits) * 2 + v * 16;
+      st_cluster_v4(map_to_cta(hbuf_local + off, dst), val);
+    }
+    if (y_bf16 != nullptr) {
+      for (int i = threadIdx.x; i < kLstmNB * Cfg::kVecPerRow; i += Cfg::kThreads) {
+        const int n = i / Cfg::kVecPerRow, v = i - n * Cfg::kVecPerRow;
+        if (b0 + n < B) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stage_raw + (n * Cfg::kUnits) * 2 + v * 16);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y_bf16) +
+                                    ((static_cast<int64_t>(b0 + n) * T + t) * (2 * H) + dir * H + rank * Cfg::kUnits) * 2 +
+                                    v * 16) = val;
+        }
+      }
+    }
+    cluster_sync_all();
+  }
+}
+
+template <int H>
+static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_bf16, float* y_f32, cudaStream_t stream) {
+  using Cfg = LstmCfg<H>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kLstmCluster, (B + kLstmNB - 1) / kLstmNB, 2);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kLstmCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  WFL_CUDA(cudaLaunchKernelEx(&cfg, lstm_kernel<H>, gx, static_cast<const __nv_bfloat16*>(whh), B, T,
+                              static_cast<__nv_bfloat16*>(y_bf16), y_f32));
+  return WFL_OK;
+}
+
+}  // namespace wfl
+
+extern "C" int wfl_lstm_layer(const float* gx, const void* whh_bf16, int32_t B, int32_t T, int32_t H, void* y_bf16,
+                              float* y_f32, void* stream_) {
+  using namespace wfl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  WFL_CHECK_ARG(gx && whh_bf16 && (y_bf16 || y_f32), "wfl_lstm_layer: null pointer");
+  WFL_CHECK_ARG(B >= 1 && T >= 1, "wfl_lstm_layer: empty problem");
+  switch (H) {
+    case 192: return launch_lstm<192>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 256: return launch_lstm<256>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 384: return launch_lstm<384>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    default:
+      set_error("wfl_lstm_layer: hidden size %d not built yet (supported: 192, 256, 384)", H);
+      return WFL_ERR_UNSUPPORTED;
+  }
+}

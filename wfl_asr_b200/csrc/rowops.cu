@@ -7,9 +7,10 @@
 
 namespace wfl {
 
-constexpr int kLnMaxVec = 12;  // float4 per lane -> d <= 1536
+constexpr int kLnMaxVecLimit = 12;  // float4 per lane -> d <= 1536
 
 // K8. nn.LayerNorm semantics (TORCH layer_norm: biased variance, eps inside the sqrt), fp32 statistics.
+template <int kLnMaxVec>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t rows, int d,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
@@ -210,13 +211,22 @@ extern "C" int wfl_layernorm(const float* x, int64_t rows, int32_t d, const floa
                              void* stream) {
   WFL_CHECK_ARG(x && gamma && beta, "wfl_layernorm: null input");
   WFL_CHECK_ARG(out_f32 || out_bf16, "wfl_layernorm: no output requested");
-  WFL_CHECK_ARG(d > 0 && d % 4 == 0 && d <= kLnMaxVec * 128, "wfl_layernorm: d=%d must be a multiple of 4, <= %d", d,
-                kLnMaxVec * 128);
+  WFL_CHECK_ARG(d > 0 && d % 4 == 0 && d <= kLnMaxVecLimit * 128, "wfl_layernorm: d=%d must be a multiple of 4, <= %d", d,
+                kLnMaxVecLimit * 128);
   WFL_CHECK_ARG((gamma2 == nullptr) == (beta2 == nullptr), "wfl_layernorm: gamma2/beta2 must come together");
   if (rows <= 0) return WFL_OK;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  layernorm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, static_cast<__nv_bfloat16*>(out_bf16));
+  // registers scale with the per-lane vector count, so pick the smallest instantiation (occupancy = bytes in flight)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  if (d <= 512)
+    layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
+  else if (d <= 768)
+    layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
+  else if (d <= 1024)
+    layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
+  else
+    layernorm_kernel<12><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }

@@ -73,3 +73,16 @@ def randomize_batchnorm(model, seed=1):
                 mod.weight.copy_(1.0 + 0.1 * torch.randn(mod.weight.shape, generator=g))
                 mod.bias.copy_(0.1 * torch.randn(mod.bias.shape, generator=g))
     return model
+
+
+def bench_model(cls, cfg, labels, seed=0, classifier_gain=60.0):
+    """Random-init model of the named architecture (torch.manual_seed(seed)) with randomised BatchNorm statistics.
+    The classifier is scaled by ``classifier_gain`` so that random-init logits are peaked enough for frames to clear
+    the 0.5 confidence threshold -- otherwise every frame decodes to "O" and the median/BIO/merge kernels would be
+    benchmarked on empty output.  Same weights for the CUDA arm and the CPU reference arm."""
+    torch.manual_seed(seed)
+    model = randomize_batchnorm(cls(cfg, labels), seed + 1)
+    with torch.no_grad():
+        model.classifier.weight.mul_(classifier_gain)
+        model.classifier.bias.mul_(classifier_gain)
+    return model
