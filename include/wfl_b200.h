@@ -45,7 +45,7 @@ int wfl_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * paired-row view of A.  Replaces: every nn.Linear / nn.Conv1d of REF/model.py:9-16,26-38,98,
  * 126-142 and of TF/models/whisper/modeling_whisper.py:567-568 + attention/MLP projections.
  */
-#define WFL_MAX_SLABS 32
+#define WFL_MAX_SLABS 128
 
 enum wfl_act { WFL_ACT_NONE = 0, WFL_ACT_GELU = 1, WFL_ACT_RELU = 2 };
 enum wfl_out_mode {
@@ -93,11 +93,31 @@ int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int
 /* ---- K8: LayerNorm (fp32 statistics) ----------------------------------------------------------
  * y = LN(x; gamma, beta); out_f32 (nullable) receives y; out_bf16 (nullable) receives y, or
  * LN(y; gamma2, beta2) when gamma2 != NULL (REF/model.py:43-44: x = ln1(x + attn); ln2(x)).
- * out_f32 may alias x.  nn.LayerNorm eps = 1e-5 everywhere on the path.
+ * out_f32 may alias x.  nn.LayerNorm eps = 1e-5 everywhere on the path.  act_bf16 = WFL_ACT_GELU applies
+ * GELU to the bf16 output only (WavLM-large conv layers: conv -> LayerNorm -> GELU,
+ * TF/models/wavlm/modeling_wavlm.py:703-727).
  */
 int wfl_layernorm(const float* x, int64_t rows, int32_t d, const float* gamma, const float* beta,
                   const float* gamma2, const float* beta2, float eps, float* out_f32, void* out_bf16,
-                  void* stream);
+                  int32_t act_bf16, void* stream);
+
+/* ---- K3: WavLM conv layer 0 (TF/models/wavlm/modeling_wavlm.py:730-751 group / :703-727 layer) ----------
+ * Conv1d(1, 512, k=10, s=5, no bias) + {norm_mode 0: GroupNorm(512 groups) = per-channel statistics over all
+ * T0 = (n_samples-10)/5+1 frames of each clip; norm_mode 1: zero-mean/unit-variance waveform
+ * (TF/models/wav2vec2/feature_extraction_wav2vec2.py:77-97) then LayerNorm over channels} + GELU.
+ * wave fp32 [B][wave_stride]; w fp32 [512][10]; out bf16 [B][out_batch_stride] rows of 512 channels.
+ * scratch_stats: (2 + 1024) * B doubles.  The pre-norm activations are recomputed, never stored.
+ */
+int wfl_wavlm_conv0(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, const float* w,
+                    const float* gamma, const float* beta, int32_t norm_mode, void* out_bf16,
+                    int64_t out_batch_stride, double* scratch_stats, void* stream);
+
+/* ---- K10: WavLM gated relative position bias gate (TF/models/wavlm/modeling_wavlm.py:159-176) -------------
+ * gate[b][h][t] = ga * (gb * gate_const[h] - 1) + 2, (ga, gb) = sigmoid(sum over 4 of Linear(hd -> 8)(x[b,t,head h])).
+ * x bf16 [B*T][row_stride]; gate_w fp32 [8][hd]; gate fp32 [B][H][T] (input of wfl_attention).
+ */
+int wfl_wavlm_gate(const void* x_bf16, int64_t row_stride, int32_t B, int32_t T, int32_t H, int32_t hd,
+                   const float* gate_w, const float* gate_b, const float* gate_const, float* gate, void* stream);
 
 /* fp32 [rows][d] -> bf16 [rows][2d] = [hi | lo] with hi = bf16(x), lo = bf16(x - hi): operands for the
  * split-precision (3-slab) tail GEMMs (classifier REF/model.py:135,192). */
@@ -111,6 +131,14 @@ int wfl_broadcast_rows(const float* src, int64_t rows, int32_t d, int32_t batche
  * boundary-offset head (REF/model.py:140-141,193).  x bf16 [rows][d], w fp32 [n_out][d]. */
 int wfl_rowdot_sigmoid(const void* x_bf16, int64_t rows, int32_t d, const float* w, const float* b, int32_t n_out,
                        float* out, void* stream);
+
+/* ---- K11: bidirectional LSTM recurrence (persistent cluster kernel; nn.LSTM at REF/model.py:105-111,183) ----
+ * One layer, both directions.  gx fp32 [B][T][8H] = x W_ih^T + b_ih + b_hh computed by wfl_gemm with the
+ * output columns packed [dir][unit][gate i,f,g,o]; whh bf16 [2][4H][H] (nn.LSTM row order, gate-major).
+ * Writes h_t as [B][T][2H] = [fwd | bwd] to y_bf16 and/or y_f32 (either may be NULL).  h0 = c0 = 0.
+ */
+int wfl_lstm_layer(const float* gx, const void* whh_bf16, int32_t B, int32_t T, int32_t H, void* y_bf16,
+                   float* y_f32, void* stream);
 
 /* ---- K0: peak normalisation (REF/infer.py:234-235 and per chunk :114-115) ---------------------
  * out[i] = (float)(in[i] / (max|in| + 1e-8)) per clip, division in fp64 like the reference's numpy

@@ -35,8 +35,9 @@ CASES = {
     "whisper_base_full": (dict(), 2, 2, 3.0, 11),
     "whisper_base_cfg2": (dict(enable_bilstm=False, enable_dilated_conv=False, num_conformer_layers=4), 2, 1, 2.0, 12),
     "wavlm_base_plus": (dict(encoder_type="wavlm", enable_bilstm=False, enable_dilated_conv=False), 2, 2, 2.0, 13),
+    # conformer_heads=4 -> head_dim 256 (heads=2 at d=1024 needs the head_dim-512 attention variant, not built yet)
     "wavlm_large": (dict(encoder_type="wavlm", wavlm_model="microsoft/wavlm-large", num_conformer_layers=1,
-                         enable_bilstm=False), 2, 2, 1.5, 14),
+                         conformer_heads=4, enable_bilstm=False), 2, 2, 1.5, 14),
 }
 
 

@@ -26,7 +26,8 @@ from wfl_asr_b200.pipeline import Labeler  # noqa: E402
 
 DEV = torch.device("cuda:0")
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "forward_golden.npz"))
-SUPPORTED = [n for n in mfg.CASES if os.environ.get("WFL_TEST_CASES", "") == "" or n in os.environ["WFL_TEST_CASES"]]
+_SEL = [s for s in os.environ.get("WFL_TEST_CASES", "").split(",") if s]
+SUPPORTED = [n for n in mfg.CASES if not _SEL or any(s in n for s in _SEL)]
 
 
 def _build(name):

@@ -390,3 +390,32 @@ def test_chunked_merge_golden(golden):
 def test_merge_rejects_bad_mode():
     with pytest.raises(ValueError):
         ops.merge_segments(None, None, 0, None, 0, None, "sideways", None, None)
+
+
+# ----------------------------------------------------------------------------------------- BiLSTM
+@pytest.mark.parametrize("H,B,T", [(256, 3, 50), (384, 9, 37), (192, 8, 120)])
+def test_lstm_layer(H, B, T):
+    """One bidirectional layer vs the step-by-step oracle restatement of nn.LSTM (REF/model.py:105-111)."""
+    d = 2 * H
+    g = torch.Generator().manual_seed(H + B)
+    sd = {}
+    for sfx in ("", "_reverse"):
+        s = H ** -0.5
+        sd[f"bilstm.weight_ih_l0{sfx}"] = (torch.rand(4 * H, d, generator=g) * 2 - 1) * s
+        sd[f"bilstm.weight_hh_l0{sfx}"] = ((torch.rand(4 * H, H, generator=g) * 2 - 1) * s).bfloat16().float()
+        sd[f"bilstm.bias_ih_l0{sfx}"] = (torch.rand(4 * H, generator=g) * 2 - 1) * s
+        sd[f"bilstm.bias_hh_l0{sfx}"] = (torch.rand(4 * H, generator=g) * 2 - 1) * s
+    x = torch.randn(B, T, d, generator=g)
+    ref = to.bilstm(x, sd, 1)
+    # gx computed in fp32 on the host side of the test so that only the recurrence kernel is under test
+    cols = []
+    for sfx in ("", "_reverse"):
+        gx = x @ sd[f"bilstm.weight_ih_l0{sfx}"].T + sd[f"bilstm.bias_ih_l0{sfx}"] + sd[f"bilstm.bias_hh_l0{sfx}"]
+        cols.append(gx.view(B, T, 4, H).permute(0, 1, 3, 2).reshape(B, T, 4 * H))  # [unit][gate]
+    gx = torch.cat(cols, dim=-1).contiguous().to(DEV)
+    whh = torch.stack([sd["bilstm.weight_hh_l0"], sd["bilstm.weight_hh_l0_reverse"]]).to(DEV).bfloat16().contiguous()
+    y16 = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    y32 = torch.full((B, T, d), float("nan"), device=DEV)
+    ops.lstm_layer(gx, whh, B, T, H, y_bf16=y16, y_f32=y32)
+    _report("lstm f32", y32, ref.to(DEV), 1.5e-2)  # h_{t-1} enters the recurrent product in bf16
+    _report("lstm bf16", y16, ref.to(DEV), 2e-2)

@@ -37,6 +37,14 @@ for w in which:
         s1 = torch.empty(B, 3000, 80, device=dev); s2 = torch.empty(B, device=dev)
         ms = t_ms(lambda: ops.whisper_logmel(wave, 480000, basis, filt, 80, out, s1, s2))
         print(f"logmel: {ms:.3f} ms")
+    elif w.startswith("lstm"):
+        # lstmH_B : one bidirectional layer, T = 1500
+        H, Bl = (int(v) for v in w[4:].split("_"))
+        gx = (torch.randn(Bl, T, 8 * H, generator=g) * 0.5).to(dev)
+        whh = (torch.randn(2, 4 * H, H, generator=g) * H ** -0.5).to(dev).bfloat16()
+        y = torch.empty(Bl, T, 2 * H, device=dev)
+        ms = t_ms(lambda: ops.lstm_layer(gx, whh, Bl, T, H, y_f32=y))
+        print(f"{w}: {ms:.3f} ms  {ms * 1e3 / T:.3f} us/step")
     elif w.startswith("gemm"):
         # gemmN_K[_mode]
         parts = w[4:].split("_"); N, K = int(parts[0]), int(parts[1]); mode = int(parts[2]) if len(parts) > 2 else 0

@@ -6,7 +6,7 @@ import os
 from . import build as _build
 
 _C = ctypes
-WFL_MAX_SLABS = 32
+WFL_MAX_SLABS = 128
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 OUT_STORE_BF16, OUT_STORE_F32, OUT_ADD_F32, OUT_GLU_BF16 = 0, 1, 2, 3
@@ -48,7 +48,7 @@ SIGNATURES = {
     "wfl_device_info": [_P, _P, _P],
     "wfl_gemm": [_C.POINTER(GemmDesc), _P],
     "wfl_attention": [_P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _I64, _I64, _P],
-    "wfl_layernorm": [_P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _P],
+    "wfl_layernorm": [_P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _I32, _P],
     "wfl_split_bf16": [_P, _I64, _I32, _P, _P],
     "wfl_broadcast_rows": [_P, _I64, _I32, _I32, _P, _P],
     "wfl_rowdot_sigmoid": [_P, _I64, _I32, _P, _P, _I32, _P, _P],
@@ -59,10 +59,9 @@ SIGNATURES = {
     "wfl_bio_decode": [_P, _P, _P, _I32, _I64, _P, _P, _I32, _D, _P, _P, _P, _P],
     "wfl_merge_segments": [_P, _P, _I64, _P, _I32, _P, _I32, _P, _P, _P],
     "wfl_htk_times": [_P, _I64, _P, _P, _P],
-    "wfl_lstm_layer": [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P],
-    "wfl_wavlm_conv0": [_P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _P, _I64, _P, _P],
-    "wfl_wavlm_gate": [_P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P],
-    "wfl_wavlm_rownorm": [_P, _I64, _I32, _I32, _P, _P, _P],
+    "wfl_lstm_layer": [_P, _P, _I32, _I32, _I32, _P, _P, _P],
+    "wfl_wavlm_conv0": [_P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _I64, _P, _P],
+    "wfl_wavlm_gate": [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
 }
 NOARG = {"wfl_abi_version": _C.c_int, "wfl_last_error": _C.c_char_p}
 

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma2,
                                                         const float* __restrict__ beta2, float eps,
                                                         float* __restrict__ out_f32,
-                                                        __nv_bfloat16* __restrict__ out_bf16) {
+                                                        __nv_bfloat16* __restrict__ out_bf16, int act) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -57,8 +57,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
       v[i].z = (v[i].z - mean) * rstd * g.z + b.z;
       v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * d)[idx] = v[i];
+      if (act == WFL_ACT_GELU) {  // bf16 branch only: act(LN(x)), optionally followed by the second LayerNorm
+        v[i].x = gelu_erf(v[i].x);
+        v[i].y = gelu_erf(v[i].y);
+        v[i].z = gelu_erf(v[i].z);
+        v[i].w = gelu_erf(v[i].w);
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
   if (out_bf16 == nullptr) return;
@@ -208,8 +214,9 @@ using namespace wfl;
 
 extern "C" int wfl_layernorm(const float* x, int64_t rows, int32_t d, const float* gamma, const float* beta,
                              const float* gamma2, const float* beta2, float eps, float* out_f32, void* out_bf16,
-                             void* stream) {
+                             int32_t act_bf16, void* stream) {
   WFL_CHECK_ARG(x && gamma && beta, "wfl_layernorm: null input");
+  WFL_CHECK_ARG(act_bf16 == WFL_ACT_NONE || act_bf16 == WFL_ACT_GELU, "wfl_layernorm: act_bf16 must be NONE or GELU");
   WFL_CHECK_ARG(out_f32 || out_bf16, "wfl_layernorm: no output requested");
   WFL_CHECK_ARG(d > 0 && d % 4 == 0 && d <= kLnMaxVecLimit * 128, "wfl_layernorm: d=%d must be a multiple of 4, <= %d", d,
                 kLnMaxVecLimit * 128);
@@ -220,13 +227,13 @@ extern "C" int wfl_layernorm(const float* x, int64_t rows, int32_t d, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
   if (d <= 512)
-    layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
+    layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
   else if (d <= 768)
-    layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
+    layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
   else if (d <= 1024)
-    layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
+    layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
   else
-    layernorm_kernel<12><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob);
+    layernorm_kernel<12><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }

@@ -119,14 +119,89 @@ class Engine:
         self._pack_ln("enc.ln", sd, "encoder.layer_norm")
 
     def _pack_wavlm(self, sd):
-        raise NotImplementedError("WavLM encoder path is not built yet")
+        """TF/models/wavlm/modeling_wavlm.py weights -> kernel layouts (conv taps, weight-norm fold, grouped pos-conv
+        as 16 implicit GEMMs, q/k/v concatenation)."""
+        a, d, c = self.arch, self.d, _arch.WAVLM_CONV
+        fe = "encoder.feature_extractor.conv_layers."
+        self._put("wl.c0.w", sd[fe + "0.conv.weight"].float()[:, 0, :])  # [512, 10]
+        self._pack_ln("wl.c0.ln", sd, fe + "0.layer_norm")
+        for i in range(1, 7):
+            self._put(f"wl.c{i}.w", packing.conv_taps(sd[fe + f"{i}.conv.weight"].float()), "bf16")
+            if a["norm"] == "layer":
+                self._pack_ln(f"wl.c{i}.ln", sd, fe + f"{i}.layer_norm")
+        self._pack_ln("wl.fp.ln", sd, "encoder.feature_projection.layer_norm")
+        self._pack_linear("wl.fp", sd["encoder.feature_projection.projection.weight"],
+                          sd["encoder.feature_projection.projection.bias"])
+        pc = "encoder.encoder.pos_conv_embed.conv."
+        g = sd[pc + "parametrizations.weight.original0"].float()
+        v = sd[pc + "parametrizations.weight.original1"].float()
+        w = v * (g / v.norm(dim=(0, 1), keepdim=True))  # weight_norm(dim=2): [d, d/16, 128]
+        bias = sd[pc + "bias"].float()
+        G, K = c["pos_groups"], c["pos_k"]
+        cg = d // G
+        for gi in range(G):
+            wt = w[gi * cg:(gi + 1) * cg].permute(0, 2, 1)  # [cg out, 128 taps, cg in]
+            wp = wt.new_zeros(cg, K, 64)  # each tap is one 64-wide K slab; channels past cg belong to the next group -> 0
+            wp[:, :, :cg] = wt
+            self._put(f"wl.pos{gi}.w", wp.reshape(cg, K * 64), "bf16")
+            self._put(f"wl.pos{gi}.b", bias[gi * cg:(gi + 1) * cg])
+        self._pack_ln("wl.enc.ln", sd, "encoder.encoder.layer_norm")
+        for i in range(a["layers"]):
+            p, q = f"encoder.encoder.layers.{i}.attention.", f"wl{i}."
+            self._pack_linear(q + "qkv", torch.cat([sd[p + f"{n}_proj.weight"].float() for n in "qkv"], 0),
+                              torch.cat([sd[p + f"{n}_proj.bias"].float() for n in "qkv"], 0))
+            self._pack_linear(q + "out", sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+            self._put(q + "gate.w", sd[p + "gru_rel_pos_linear.weight"])
+            self._put(q + "gate.b", sd[p + "gru_rel_pos_linear.bias"])
+            self._put(q + "gate.c", sd[p + "gru_rel_pos_const"].float().reshape(-1))
+            p = f"encoder.encoder.layers.{i}."
+            self._pack_ln(q + "ln1", sd, p + "layer_norm")
+            self._pack_ln(q + "ln2", sd, p + "final_layer_norm")
+            self._pack_linear(q + "fc1", sd[p + "feed_forward.intermediate_dense.weight"],
+                              sd[p + "feed_forward.intermediate_dense.bias"])
+            self._pack_linear(q + "fc2", sd[p + "feed_forward.output_dense.weight"],
+                              sd[p + "feed_forward.output_dense.bias"])
+        self._put("wl.rel_emb", sd["encoder.encoder.layers.0.attention.rel_attn_embed.weight"])  # [320, H]
+        self._rel_tables = {}
+
+    def _rel_bias_table(self, T):
+        """[H][2T-1] table of the bucketed relative position embedding over rel = key - query
+        (TF/models/wavlm/modeling_wavlm.py:243-271), built once per sequence length."""
+        tab = self._rel_tables.get(T)
+        if tab is None:
+            c = _arch.WAVLM_CONV
+            nb = c["num_buckets"] // 2
+            max_exact = nb // 2
+            rel = torch.arange(-(T - 1), T, dtype=torch.long)
+            bucket = (rel > 0).long() * nb
+            r = rel.abs()
+            large = torch.log(r.float() / max_exact) / math.log(c["max_distance"] / max_exact) * (nb - max_exact)
+            large = torch.min((max_exact + large).long(), torch.full_like(r, nb - 1))
+            bucket = bucket + torch.where(r < max_exact, r, large)
+            tab = self.W["wl.rel_emb"][bucket.to(self.dev)].t().contiguous()  # [H, 2T-1]
+            self._rel_tables = {T: tab}
+        return tab
 
     def _pack_bilstm(self, sd):
-        raise NotImplementedError("BiLSTM path is not built yet")
+        """nn.LSTM weights (REF/model.py:105-111): W_ih rows re-ordered [unit][gate] per direction so the recurrence
+        reads its four gate pre-activations as one float4; b_ih + b_hh folded into the input GEMM's bias."""
+        d = self.d
+        Hs = d // 2
+        self.lstm_layers = self.m.get("bilstm_num_layer", 1)
+        for layer in range(self.lstm_layers):
+            w_in, b_in, w_hh = [], [], []
+            for suffix in ("", "_reverse"):
+                w_ih = sd[f"bilstm.weight_ih_l{layer}{suffix}"].float()
+                w_in.append(w_ih.view(4, Hs, -1).permute(1, 0, 2).reshape(4 * Hs, -1))
+                b = sd[f"bilstm.bias_ih_l{layer}{suffix}"].float() + sd[f"bilstm.bias_hh_l{layer}{suffix}"].float()
+                b_in.append(b.view(4, Hs).t().reshape(-1))
+                w_hh.append(sd[f"bilstm.weight_hh_l{layer}{suffix}"].float())
+            self._pack_linear(f"lstm{layer}.in", torch.cat(w_in, 0), torch.cat(b_in, 0))
+            self._put(f"lstm{layer}.whh", torch.stack(w_hh, 0), "bf16")
 
     # ------------------------------------------------------------------------------------ workspaces
-    def _buffers(self, B, T):
-        key = (B, T)
+    def _buffers(self, B, T, n_samples=None):
+        key = (B, T, n_samples)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -146,14 +221,33 @@ class Engine:
             "logits": torch.empty(B, T, self.Lp, device=dev),
             "offsets": torch.empty(B, T, 2, device=dev),
         }
+        if self.m.get("enable_bilstm", True):
+            ws["gx"] = torch.empty(M, 4 * d, device=dev)
         if self.arch["type"] == "whisper":
             ws["wave"] = torch.zeros(B, 480000, device=dev)
             ws["feats"] = torch.empty(B, 3000, MEL_PAD, **bf)
             ws["h1"] = torch.empty(B, 3000, d, **bf)
             ws["logspec"] = torch.empty(B, 3000, self.arch["mels"], device=dev)
             ws["smax"] = torch.empty(B, device=dev)
+        elif n_samples is not None:
+            Ts = self._wavlm_lengths(n_samples)
+            large = self.arch["norm"] == "layer"
+            ws["cA"] = torch.empty(B * Ts[0] + 2, 512, **bf)  # conv activations ping-pong (+ spill rows of the paired view)
+            ws["cB"] = torch.empty(B * Ts[1] + 2, 512, **bf)
+            ws["cf"] = torch.empty(B * (Ts[1] if large else Ts[6]), 512, device=dev)
+            ws["h512"] = torch.empty(M, 512, **bf)
+            ws["wstats"] = torch.empty((2 + 1024) * B, dtype=torch.float64, device=dev)
+            ws["gate"] = torch.empty(B, self.arch["heads"], T, device=dev)
         self._ws = {key: ws}  # keep one shape resident (batches of one shape dominate bulk labeling)
         return ws
+
+    @staticmethod
+    def _wavlm_lengths(n):
+        out = []
+        for k, s in zip(_arch.WAVLM_CONV["kernels"], _arch.WAVLM_CONV["strides"]):
+            n = (n - k) // s + 1
+            out.append(n)
+        return out
 
     # ------------------------------------------------------------------------------------ building blocks
     def _linear(self, a, name, out, M, K, **kw):
@@ -210,6 +304,85 @@ class Engine:
             self._linear(ws["u"], q + "fc2", x, M, a["ffn"], out_mode=ops.OUT_ADD_F32)
         return T
 
+    def _wavlm_encoder(self, wave, B):
+        """REF/model.py:159-161 -> TF/models/wavlm/modeling_wavlm.py:1039-1095 with attention_mask=None.
+        wavlm-base(-plus): GroupNorm conv0, post-LN layers; wavlm-large: LayerNorm convs, pre-LN layers."""
+        a, d, c = self.arch, self.d, _arch.WAVLM_CONV
+        n = wave.shape[1]
+        Ts = self._wavlm_lengths(n)
+        if Ts[-1] < 1:
+            raise ValueError(f"clip of {n} samples is shorter than WavLM's receptive field")
+        T = Ts[6]
+        M = B * T
+        ws = self._buffers(B, T, n)
+        if wave.dtype != torch.float32 or not wave.is_contiguous():
+            wave = wave.float().contiguous()
+        large = a["norm"] == "layer"
+        # conv0 (k10, s5) + GroupNorm-over-time | (input normalisation + LayerNorm) + GELU
+        ops.wavlm_conv0(wave, n, self.W["wl.c0.w"], self.W["wl.c0.ln.g"], self.W["wl.c0.ln.b"], 1 if large else 0,
+                        ws["cA"], Ts[0] * 512, ws["wstats"])
+        src, dst = ws["cA"], ws["cB"]
+        for i in range(1, 7):
+            k = c["kernels"][i]
+            t_in, t_out = Ts[i - 1], Ts[i]
+            # stride-2 conv over the paired-row view [ceil(t_in/2), 1024]: taps 0,1 = the pair, tap 2 = next pair's first
+            shifts, cols = ([0, 0, 1], [0, 512, 0]) if k == 3 else ([0, 0], [0, 512])
+            last = i == 6
+            common = dict(n=512, slab_k=512, shifts=shifts, cols=cols, a_rows=(t_in + 1) // 2, a_cols=1024,
+                          a_row_stride=1024, a_batch_stride=t_in * 512, batches=B, m_rows=t_out, out_row_stride=512,
+                          out_batch_stride=t_out * 512)
+            if large:
+                ops.gemm(src, self.W[f"wl.c{i}.w"], ws["cf"], out_mode=ops.OUT_STORE_F32, **common)
+                g1, b1 = self.W[f"wl.c{i}.ln.g"], self.W[f"wl.c{i}.ln.b"]
+                if last:  # LayerNorm + GELU, then the feature-projection LayerNorm, in one pass
+                    ops.layernorm(ws["cf"], g1, b1, gamma2=self.W["wl.fp.ln.g"], beta2=self.W["wl.fp.ln.b"],
+                                  out_bf16=ws["h512"], act_bf16=ops.ACT_GELU, rows=B * t_out)
+                else:
+                    ops.layernorm(ws["cf"], g1, b1, out_bf16=dst, act_bf16=ops.ACT_GELU, rows=B * t_out)
+            elif last:
+                ops.gemm(src, self.W[f"wl.c{i}.w"], ws["cf"], act=ops.ACT_GELU, out_mode=ops.OUT_STORE_F32, **common)
+                ops.layernorm(ws["cf"], self.W["wl.fp.ln.g"], self.W["wl.fp.ln.b"], out_bf16=ws["h512"], rows=M)
+            else:
+                ops.gemm(src, self.W[f"wl.c{i}.w"], dst, act=ops.ACT_GELU, **common)
+            src, dst = dst, src
+        # feature projection -> fp32 hidden states
+        x = ws["x"]
+        self._linear(ws["h512"], "wl.fp", x, M, 512, out_mode=ops.OUT_STORE_F32)
+        # positional conv (k128, pad 64, 16 groups, weight-norm folded) + GELU, added to x: one implicit GEMM per group
+        ops.split_bf16(x, ws["hl"])
+        G, K = c["pos_groups"], c["pos_k"]
+        cg = d // G
+        x3 = x.view(B, T, d)
+        for gi in range(G):
+            ops.gemm(ws["hl"], self.W[f"wl.pos{gi}.w"], x3[:, :, gi * cg:], n=cg, slab_k=64,
+                     shifts=[j - K // 2 for j in range(K)], cols=[gi * cg] * K, a_rows=T, a_cols=d, a_row_stride=2 * d,
+                     a_batch_stride=T * 2 * d, batches=B, m_rows=T, out_row_stride=d, out_batch_stride=T * d,
+                     bias=self.W[f"wl.pos{gi}.b"], act=ops.ACT_GELU, out_mode=ops.OUT_ADD_F32, tile_n=128)
+        H = a["heads"]
+        hd = d // H
+        tab = self._rel_bias_table(T)
+        if not large:
+            self._ln(x, "wl.enc.ln", out_f32=x, out_bf16=ws["h"])
+        for i in range(a["layers"]):
+            q = f"wl{i}."
+            if large:
+                self._ln(x, q + "ln1", out_bf16=ws["h"])
+            self._linear(ws["h"], q + "qkv", ws["qkv"], M, d)
+            ops.wavlm_gate(ws["h"], d, B, T, H, hd, self.W[q + "gate.w"], self.W[q + "gate.b"], self.W[q + "gate.c"],
+                           ws["gate"])
+            ops.attention(ws["qkv"].view(B, T, 3 * d), ws["ctx"].view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5,
+                          q_col=0, k_col=d, v_col=2 * d, rel_bias=tab, gate=ws["gate"])
+            self._linear(ws["ctx"], q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
+            if large:
+                self._ln(x, q + "ln2", out_bf16=ws["h"])
+            else:
+                self._ln(x, q + "ln1", out_f32=x, out_bf16=ws["h"])
+            self._linear(ws["h"], q + "fc1", ws["u"], M, d, act=ops.ACT_GELU)
+            self._linear(ws["u"], q + "fc2", x, M, a["ffn"], out_mode=ops.OUT_ADD_F32)
+            if not large:
+                self._ln(x, q + "ln2", out_f32=x, out_bf16=ws["h"])
+        return ws, T
+
     # ------------------------------------------------------------------------------------ conformer
     def _conformer(self, i, ws, B, T):
         """REF/model.py:40-52 on the fp32 residual stream x."""
@@ -256,12 +429,19 @@ class Engine:
             T = self._whisper_encoder(wave, ws, B)
             final_ln = "enc.ln"
         else:
-            raise NotImplementedError("WavLM encoder path is not built yet")
+            ws, T = self._wavlm_encoder(wave, B)
+            # wavlm-large ends with encoder.layer_norm; wavlm-base(-plus) is post-LN: x is final and ws["h"] = bf16(x)
+            final_ln = "wl.enc.ln" if self.arch["stable_ln"] else None
         x = ws["x"]
         M = B * T
-        if max_label_len is not None:
+        bilstm = self.m.get("enable_bilstm", True)
+        if final_ln is None and max_label_len is None:
+            if lang_id is not None:
+                self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
+        elif max_label_len is not None:
             # REF/model.py:166-174 (training/eval only): fix T to the label length; rare path, torch glue
-            self._ln(x, final_ln, out_f32=x)
+            if final_ln is not None:
+                self._ln(x, final_ln, out_f32=x)
             mll = int(max_label_len)
             if mll < T:
                 xs = x[:, :mll].contiguous()
@@ -270,16 +450,28 @@ class Engine:
             ws = self._buffers(B, mll)
             ws["x"].copy_(xs)
             x, T, M = ws["x"], mll, B * mll
+            ops.split_bf16(x, ws["hl"])
             if lang_id is not None:
-                ops.split_bf16(x, ws["hl"])
-                self._lang_proj(ws["hl"], 2 * d, lang_id, ws, B, T)
+                self._lang_proj(ws["hl"], 2 * d, lang_id, ws, B, T, bilstm)
+            elif bilstm:
+                ws["h"].view(B, T, d).copy_(ws["hl"].view(B, T, 2 * d)[:, :, :d])
         elif lang_id is not None:
             self._ln(x, final_ln, out_bf16=ws["h"])
-            self._lang_proj(ws["h"], d, lang_id, ws, B, T)
+            self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
+        elif bilstm:
+            self._ln(x, final_ln, out_bf16=ws["h"])
         else:
             self._ln(x, final_ln, out_f32=x)
-        if self.m.get("enable_bilstm", True):
-            raise NotImplementedError("BiLSTM path is not built yet")
+        if bilstm:
+            # REF/model.py:182-183: input projection for all steps as one GEMM, then the serial recurrence
+            a_in = ws["h"]
+            Hs = d // 2
+            for layer in range(self.lstm_layers):
+                last = layer == self.lstm_layers - 1
+                self._linear(a_in, f"lstm{layer}.in", ws["gx"], M, d, out_mode=ops.OUT_STORE_F32)
+                ops.lstm_layer(ws["gx"], self.W[f"lstm{layer}.whh"], B, T, Hs,
+                               y_bf16=None if last else ws["ctx"], y_f32=x if last else None)
+                a_in = ws["ctx"]
         for i in range(self.n_conf):
             self._conformer(i, ws, B, T)
         # tail: dilated stack -> classifier (split precision) + boundary-offset head
@@ -302,13 +494,15 @@ class Engine:
         ops.rowdot_sigmoid(ws["c"], self.W["off.w"], self.W["off.b"], ws["offsets"])
         return ws["logits"][:, :, :self.L], ws["offsets"]
 
-    def _lang_proj(self, a, a_row_stride, lang_id, ws, B, T):
-        """REF/model.py:176-180 folded: x = W_h h + (W_e emb[lang] + b), one bias row per batch item."""
+    def _lang_proj(self, a, a_row_stride, lang_id, ws, B, T, to_bf16=False):
+        """REF/model.py:176-180 folded: x = W_h h + (W_e emb[lang] + b), one bias row per batch item.  The result feeds
+        the BiLSTM input GEMM (bf16, ws["h"]) or becomes the fp32 residual stream (ws["x"])."""
         d = self.d
         lang_id = lang_id.to(self.dev).long().view(-1)
         if lang_id.numel() != B:
             raise ValueError("lang_id must have one entry per batch item")
         bias = self.W["lang.bias"].index_select(0, lang_id).contiguous()  # [B, d]
-        ops.gemm(a, self.W["lang.w"], ws["x"], n=d, slab_k=d, a_rows=T, a_cols=d, a_row_stride=a_row_stride,
-                 a_batch_stride=T * a_row_stride, batches=B, m_rows=T, out_row_stride=d, out_batch_stride=T * d,
-                 bias=bias, bias_batch_stride=d, out_mode=ops.OUT_STORE_F32)
+        ops.gemm(a, self.W["lang.w"], ws["h"] if to_bf16 else ws["x"], n=d, slab_k=d, a_rows=T, a_cols=d,
+                 a_row_stride=a_row_stride, a_batch_stride=T * a_row_stride, batches=B, m_rows=T, out_row_stride=d,
+                 out_batch_stride=T * d, bias=bias, bias_batch_stride=d,
+                 out_mode=ops.OUT_STORE_BF16 if to_bf16 else ops.OUT_STORE_F32)

@@ -79,11 +79,27 @@ def attention(qkv, out, *, B, T, H, hd, scale, q_col, k_col, v_col, rel_bias=Non
     _count()
 
 
-def layernorm(x, gamma, beta, *, out_f32=None, out_bf16=None, gamma2=None, beta2=None, eps=1e-5):
-    rows = x.numel() // x.shape[-1]
+def layernorm(x, gamma, beta, *, out_f32=None, out_bf16=None, gamma2=None, beta2=None, eps=1e-5, act_bf16=ACT_NONE,
+              rows=None):
+    rows = x.numel() // x.shape[-1] if rows is None else rows
     rc = _lib.load().wfl_layernorm(_ptr(x), rows, x.shape[-1], _ptr(gamma), _ptr(beta), _ptr(gamma2), _ptr(beta2), eps,
-                                   _ptr(out_f32), _ptr(out_bf16), _stream())
+                                   _ptr(out_f32), _ptr(out_bf16), act_bf16, _stream())
     _lib.check(rc, "wfl_layernorm")
+    _count()
+
+
+def wavlm_conv0(wave, n_samples, w, gamma, beta, norm_mode, out, out_batch_stride, scratch):
+    """wave fp32 [B, >=n_samples] -> out bf16 [B, out_batch_stride/512 rows, 512] (conv k10 s5 + norm + GELU)."""
+    rc = _lib.load().wfl_wavlm_conv0(_ptr(wave), wave.stride(0), n_samples, wave.shape[0], _ptr(w), _ptr(gamma),
+                                     _ptr(beta), norm_mode, _ptr(out), out_batch_stride, _ptr(scratch), _stream())
+    _lib.check(rc, "wfl_wavlm_conv0")
+    _count(2)
+
+
+def wavlm_gate(x_bf16, row_stride, B, T, H, hd, gw, gb, gconst, gate):
+    rc = _lib.load().wfl_wavlm_gate(_ptr(x_bf16), row_stride, B, T, H, hd, _ptr(gw), _ptr(gb), _ptr(gconst), _ptr(gate),
+                                    _stream())
+    _lib.check(rc, "wfl_wavlm_gate")
     _count()
 
 
@@ -157,4 +173,11 @@ def merge_segments(segs, nseg, clip_stride, file_clip_begin, n_files, ph_class, 
 
 def htk_times(segs, n, start_out, end_out):
     _lib.check(_lib.load().wfl_htk_times(_ptr(segs), n, _ptr(start_out), _ptr(end_out), _stream()), "wfl_htk_times")
+    _count()
+
+
+def lstm_layer(gx, whh, B, T, H, y_bf16=None, y_f32=None):
+    """gx fp32 [B, T, 8H] (columns [dir][unit][gate]); whh bf16 [2, 4H, H] -> y [B, T, 2H]."""
+    rc = _lib.load().wfl_lstm_layer(_ptr(gx), _ptr(whh), B, T, H, _ptr(y_bf16), _ptr(y_f32), _stream())
+    _lib.check(rc, "wfl_lstm_layer")
     _count()
