@@ -152,15 +152,18 @@ int wfl_peak_normalize(const double* in, const int64_t* clip_begin, int32_t n_cl
                        int64_t out_stride, double* out_f64, double* scratch_max, void* stream);
 
 /* ---- K1: Whisper log-mel front-end (TF/models/whisper/feature_extraction_whisper.py:135-164) --
- * wave fp32 [B][wave_stride] (n_samples valid, zero-extended/truncated to 480000), windowed DFT as
- * a direct contraction against basis [402][400] (rows 0..200 cos, 201..401 -sin, periodic Hann folded
- * in), power, mel (filters [201][n_mels]), log10(clamp 1e-10), per-clip max-8 floor, (x+4)/4.
- * out bf16 [B][3000][out_stride] (channels >= n_mels zeroed).  scratch: fp32 [B][3000][n_mels] +
- * B floats (clip maxima).
+ * wave fp32 [B][wave_stride] (n_samples valid, zero-extended/truncated to 480000).  The windowed DFT is a
+ * tensor-core contraction over an overlapping-row view of the reflect-padded waveform in split precision
+ * (hi*hi + hi*mid + mid*hi): basis_split_bf16 is bf16 [448][3*448] = [W_hi | W_mid | W_hi] with
+ * W[n][k] = hann[k] * {cos, -sin}(2 pi (n/2) k / 400) for output column n (cos/-sin interleaved per bin), zero padded.
+ * Then power, mel (filters fp32 [201][n_mels]), log10(clamp 1e-10), per-clip max-8 floor, (x+4)/4.
+ * out bf16 [B][3000][out_stride] (channels >= n_mels zeroed).  scratch_planes: bf16 2*480480*B + 4096 elements;
+ * scratch_dft: fp32 [B][3000][448]; scratch_logspec: fp32 [B][3000][n_mels]; scratch_max: B floats.
  */
-int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, const float* basis,
-                       const float* mel_filters, int32_t n_mels, void* out_bf16, int32_t out_stride,
-                       float* scratch_logspec, float* scratch_max, void* stream);
+int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B,
+                       const void* basis_split_bf16, const float* mel_filters, int32_t n_mels, void* out_bf16,
+                       int32_t out_stride, void* scratch_planes, float* scratch_dft, float* scratch_logspec,
+                       float* scratch_max, void* stream);
 
 /* ---- K15/K18/K19: decode -> median -> BIO -> merge --------------------------------------------- */
 typedef struct wfl_segment {

@@ -272,9 +272,9 @@ def test_whisper_logmel(n_mels):
         wave[i, :len(w)] = w
     basis, filt = whisper_frontend_constants(n_mels, DEV)
     out = torch.empty(B, 3000, 128, device=DEV, dtype=torch.bfloat16)
-    s1 = torch.empty(B, 3000, n_mels, device=DEV)
-    s2 = torch.empty(B, device=DEV)
-    ops.whisper_logmel(wave.to(DEV), 480000, basis, filt, n_mels, out, s1, s2)
+    scratch = ops.logmel_scratch(B, n_mels, DEV)
+    s1 = scratch[2]
+    ops.whisper_logmel(wave.to(DEV), 480000, basis, filt, n_mels, out, scratch)
     ref = to.whisper_log_mel(wave, n_mels).transpose(1, 2)  # [B, 3000, n_mels]
     got = out[..., :n_mels].float().cpu()
     assert not out[..., n_mels:].any()

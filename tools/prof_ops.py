@@ -34,9 +34,20 @@ for w in which:
         wave = (torch.randn(B, 480000, generator=g) * 0.1).to(dev)
         basis, filt = whisper_frontend_constants(80, dev)
         out = torch.empty(B, 3000, 128, device=dev, dtype=torch.bfloat16)
-        s1 = torch.empty(B, 3000, 80, device=dev); s2 = torch.empty(B, device=dev)
-        ms = t_ms(lambda: ops.whisper_logmel(wave, 480000, basis, filt, 80, out, s1, s2))
+        scratch = ops.logmel_scratch(B, 80, dev)
+        ms = t_ms(lambda: ops.whisper_logmel(wave, 480000, basis, filt, 80, out, scratch))
         print(f"logmel: {ms:.3f} ms")
+    elif w.startswith("conv"):
+        # convK_d[_tile]: Conformer conv module shape, K taps over [B, T, d]
+        parts = w[4:].split("_"); taps, dd = int(parts[0]), int(parts[1]); tile = int(parts[2]) if len(parts) > 2 else 0
+        xin = torch.randn(B, T, dd, generator=g).to(dev).bfloat16()
+        wt = (torch.randn(dd, taps * dd, generator=g) * (taps * dd) ** -0.5).to(dev).bfloat16()
+        o = torch.empty(B, T, dd, device=dev, dtype=torch.bfloat16); bias = torch.zeros(dd, device=dev)
+        pad = (taps - 1) // 2
+        ms = t_ms(lambda: ops.gemm(xin, wt, o, n=dd, slab_k=dd, shifts=[j - pad for j in range(taps)], cols=[0] * taps,
+                                   a_rows=T, a_cols=dd, a_row_stride=dd, a_batch_stride=T * dd, batches=B, m_rows=T,
+                                   out_row_stride=dd, out_batch_stride=T * dd, bias=bias, act=ops.ACT_GELU, tile_n=tile))
+        print(f"{w}: {ms:.4f} ms  {2.0 * B * T * dd * taps * dd / ms / 1e9:.1f} TFLOP/s")
     elif w.startswith("lstm"):
         # lstmH_B : one bidirectional layer, T = 1500
         H, Bl = (int(v) for v in w[4:].split("_"))

@@ -6,10 +6,16 @@
 //   mel[t][m]    = sum_k |X[t][k]|^2 * filt[k][m];  y = log10(max(mel, 1e-10))
 //   out          = (max(y, max_clip(y) - 8) + 4) / 4
 //
-// The DFT is a direct fp32 contraction against a [400][448] basis (cos/-sin interleaved per bin, window
-// folded in, built on the host in fp64).  It stays in fp32 on the CUDA cores on purpose: the log
-// compresses 80 dB of dynamic range, so bf16/tf32 operands (noise floor -54/-66 dB) would corrupt
-// quiet bins (DESIGN.md "precision").  CTA = 64 frames x all 201 bins; thread tile 4 frames x 14 bins.
+// The windowed DFT is a dense contraction [3000 x 400] x [400 x 402] per clip and runs on the tensor cores
+// through the slab GEMM of gemm.cu -- without materialising frames: the A operand is a tensor map over the
+// padded waveform whose rows OVERLAP (row stride = hop = 160 samples, row length 400).
+// Precision: a log over 80 dB of dynamic range cannot take bf16 operands as they are (noise floor -54 dB), so
+// both operands are split hi + mid (x = bf16(x) + bf16(x - bf16(x)), ~16 mantissa bits) and three K-slabs
+// accumulate  hi*hi + hi*mid + mid*hi  in fp32 (max feature error vs fp32 FFT ~1e-5, tests/test_ops_gpu.py).
+// The two planes sit 3003 rows apart in the same strided view, so "plane" is just a slab row shift.
+//   1. logmel_prep_kernel : wave fp32 -> reflect-padded bf16 planes [B][2][480480]
+//   2. wfl_gemm           : planes x basis[448][3*448] -> X fp32 [B][3000][448] (cos/-sin interleaved per bin)
+//   3. logmel_post_kernel : |X|^2 -> mel -> log10 -> scratch + per-clip max;  4. logmel_finish_kernel -> bf16
 #include <algorithm>
 
 #include "common.cuh"
@@ -21,11 +27,11 @@ constexpr int kHop = 160;
 constexpr int kBins = 201;
 constexpr int kFrames = 3000;
 constexpr int kPadSamples = 480000;
-constexpr int kBasisCols = 448;  // 2 * 224 >= 2 * 201, float4-friendly per-thread slice of 28
+constexpr int kPlaneRows = 3003;               // rows of the strided view per plane
+constexpr int kPlane = kPlaneRows * kHop;      // 480480 samples >= 480400 padded samples
+constexpr int kDftCols = 448;                  // 2 * 201 = 402 outputs padded to 7 x 64
 constexpr int kFrameTile = 64;
-constexpr int kSpan = (kFrameTile - 1) * kHop + kNfft;  // 10480 samples feed 64 frames
-constexpr int kKChunk = 16;
-constexpr int kPwStride = 225;  // 224 bins + 1 pad
+constexpr int kPwStride = 225;
 
 __device__ __forceinline__ unsigned float_order_key(float v) {
   const unsigned b = __float_as_uint(v);
@@ -35,73 +41,49 @@ __device__ __forceinline__ float float_from_key(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-__global__ void __launch_bounds__(256, 1)
-logmel_power_kernel(const float* __restrict__ wave, int64_t wave_stride, int n_samples,
-                    const float* __restrict__ basis, const float* __restrict__ filt, int n_mels,
-                    float* __restrict__ logspec, unsigned* __restrict__ clip_max_key) {
-  extern __shared__ float sm[];
-  float* xs = sm;                        // [kSpan]
-  float* bs = xs + kSpan;                // [kKChunk][kBasisCols]
-  float* pw = bs + kKChunk * kBasisCols; // [kFrameTile][kPwStride]
+__global__ void __launch_bounds__(256) logmel_prep_kernel(const float* __restrict__ wave, int64_t wave_stride,
+                                                          int n_samples, __nv_bfloat16* __restrict__ planes) {
+  const int b = blockIdx.y;
+  const float* w = wave + b * wave_stride;
+  const int valid = n_samples < kPadSamples ? n_samples : kPadSamples;
+  __nv_bfloat16* hi = planes + static_cast<int64_t>(b) * 2 * kPlane;
+  __nv_bfloat16* mid = hi + kPlane;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kPlane; i += gridDim.x * blockDim.x) {
+    float x = 0.f;
+    if (i < kPadSamples + kNfft) {
+      int j = i - kNfft / 2;  // torch.stft reflect padding of the zero-extended 480000-sample clip
+      if (j < 0) j = -j;
+      if (j >= kPadSamples) j = 2 * (kPadSamples - 1) - j;
+      x = j < valid ? w[j] : 0.f;
+    }
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    mid[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
 
+__global__ void __launch_bounds__(256, 2)
+logmel_post_kernel(const float* __restrict__ dft /*[B][3000][448]*/, const float* __restrict__ filt, int n_mels,
+                   float* __restrict__ logspec, unsigned* __restrict__ clip_max_key) {
+  extern __shared__ float pw[];  // [kFrameTile][kPwStride]
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFrameTile;
   const int tid = threadIdx.x;
-  const float* w = wave + b * wave_stride;
-  const int valid = n_samples < kPadSamples ? n_samples : kPadSamples;
-
-  // samples with torch's reflect padding of the zero-extended 480000-sample clip
-  for (int i = tid; i < kSpan; i += 256) {
-    int j = t0 * kHop + i - kNfft / 2;
-    if (j < 0) j = -j;
-    if (j >= kPadSamples) j = 2 * (kPadSamples - 1) - j;
-    xs[i] = (j >= 0 && j < valid) ? w[j] : 0.0f;
-  }
-
-  const int fg = tid >> 4;  // frame group: frames 4*fg .. 4*fg+3
-  const int bg = tid & 15;  // bin group: basis columns 28*bg .. 28*bg+27  (bins 14*bg .. 14*bg+13)
-  float acc[4][28];
-#pragma unroll
-  for (int f = 0; f < 4; ++f)
-#pragma unroll
-    for (int c = 0; c < 28; ++c) acc[f][c] = 0.f;
-
-  for (int n0 = 0; n0 < kNfft; n0 += kKChunk) {
-    __syncthreads();
-    for (int i = tid; i < kKChunk * kBasisCols / 4; i += 256)
-      reinterpret_cast<float4*>(bs)[i] = __ldg(reinterpret_cast<const float4*>(basis + n0 * kBasisCols) + i);
-    __syncthreads();
-#pragma unroll 4
-    for (int nn = 0; nn < kKChunk; ++nn) {
-      float xv[4];
-#pragma unroll
-      for (int f = 0; f < 4; ++f) xv[f] = xs[(4 * fg + f) * kHop + n0 + nn];
-      const float4* brow = reinterpret_cast<const float4*>(bs + nn * kBasisCols + 28 * bg);
-#pragma unroll
-      for (int q = 0; q < 7; ++q) {
-        const float4 bv = brow[q];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          acc[f][4 * q + 0] = fmaf(xv[f], bv.x, acc[f][4 * q + 0]);
-          acc[f][4 * q + 1] = fmaf(xv[f], bv.y, acc[f][4 * q + 1]);
-          acc[f][4 * q + 2] = fmaf(xv[f], bv.z, acc[f][4 * q + 2]);
-          acc[f][4 * q + 3] = fmaf(xv[f], bv.w, acc[f][4 * q + 3]);
-        }
-      }
+  // |X|^2: thread reads float2 (re, im) pairs, coalesced along the bin axis
+  for (int i = tid; i < kFrameTile * kBins; i += 256) {
+    const int f = i / kBins, k = i - f * kBins;
+    const int t = t0 + f;
+    float v = 0.f;
+    if (t < kFrames) {
+      const float2 c = *reinterpret_cast<const float2*>(dft + (static_cast<int64_t>(b) * kFrames + t) * kDftCols + 2 * k);
+      v = c.x * c.x + c.y * c.y;
     }
+    pw[f * kPwStride + k] = v;
   }
-  // |X|^2 -> smem
-#pragma unroll
-  for (int f = 0; f < 4; ++f)
-#pragma unroll
-    for (int k = 0; k < 14; ++k) {
-      const float re = acc[f][2 * k], im = acc[f][2 * k + 1];
-      pw[(4 * fg + f) * kPwStride + 14 * bg + k] = re * re + im * im;
-    }
   __syncthreads();
-
-  // mel projection + log10: thread = 4 frames x (n_mels / 16) mels
-  const int mpt = n_mels >> 4;  // 5 (80 mels) or 8 (128 mels)
+  const int fg = tid >> 4;  // 4 frames
+  const int bg = tid & 15;  // n_mels / 16 mels
+  const int mpt = n_mels >> 4;
   float m[4][8];
 #pragma unroll
   for (int f = 0; f < 4; ++f)
@@ -143,7 +125,6 @@ __global__ void __launch_bounds__(256) logmel_finish_kernel(const float* __restr
                                                             const unsigned* __restrict__ clip_max_key, int n_mels,
                                                             __nv_bfloat16* __restrict__ out, int out_stride,
                                                             int64_t total_rows) {
-  // one thread per (row, pair of output channels)
   const int pairs = out_stride >> 1;
   const int64_t total = total_rows * pairs;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -159,17 +140,19 @@ __global__ void __launch_bounds__(256) logmel_finish_kernel(const float* __restr
   }
 }
 
-constexpr int kLogmelSmem = (kSpan + kKChunk * kBasisCols + kFrameTile * kPwStride) * 4;
+constexpr int kPostSmem = kFrameTile * kPwStride * 4;
 
 }  // namespace wfl
 
 using namespace wfl;
 
 extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B,
-                                  const float* basis, const float* mel_filters, int32_t n_mels, void* out_bf16,
-                                  int32_t out_stride, float* scratch_logspec, float* scratch_max, void* stream_) {
+                                  const void* basis_split_bf16, const float* mel_filters, int32_t n_mels,
+                                  void* out_bf16, int32_t out_stride, void* scratch_planes, float* scratch_dft,
+                                  float* scratch_logspec, float* scratch_max, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  WFL_CHECK_ARG(wave && basis && mel_filters && out_bf16 && scratch_logspec && scratch_max,
+  WFL_CHECK_ARG(wave && basis_split_bf16 && mel_filters && out_bf16 && scratch_planes && scratch_dft &&
+                    scratch_logspec && scratch_max,
                 "wfl_whisper_logmel: null pointer");
   WFL_CHECK_ARG(n_mels == 80 || n_mels == 128, "wfl_whisper_logmel: n_mels must be 80 or 128 (got %d)", n_mels);
   WFL_CHECK_ARG(out_stride >= n_mels && out_stride % 8 == 0, "wfl_whisper_logmel: out_stride %d invalid", out_stride);
@@ -178,14 +161,50 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
   if (B <= 0) return WFL_OK;
   static bool configured = false;
   if (!configured) {
-    WFL_CUDA(cudaFuncSetAttribute(logmel_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLogmelSmem));
+    WFL_CUDA(cudaFuncSetAttribute(logmel_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
     configured = true;
   }
   WFL_CUDA(cudaMemsetAsync(scratch_max, 0, sizeof(unsigned) * B, stream));
-  dim3 grid((kFrames + kFrameTile - 1) / kFrameTile, B);
-  logmel_power_kernel<<<grid, 256, kLogmelSmem, stream>>>(wave, wave_stride, n_samples, basis, mel_filters, n_mels,
-                                                          scratch_logspec, reinterpret_cast<unsigned*>(scratch_max));
-  WFL_CUDA(cudaGetLastError());
+  {
+    dim3 grid(128, B);
+    logmel_prep_kernel<<<grid, 256, 0, stream>>>(wave, wave_stride, n_samples,
+                                                 static_cast<__nv_bfloat16*>(scratch_planes));
+    WFL_CUDA(cudaGetLastError());
+  }
+  {
+    // X[b, t, :] = hi_t . W_hi + hi_t . W_mid + mid_t . W_hi   (rows overlap: stride 160, length 400)
+    wfl_gemm_desc d = {};
+    d.a = scratch_planes;
+    d.a_rows = 2 * kPlaneRows;
+    d.a_cols = kNfft;
+    d.a_row_stride = kHop;
+    d.a_batch_stride = 2 * static_cast<int64_t>(kPlane);
+    d.batches = B;
+    d.w = basis_split_bf16;
+    d.n = kDftCols;
+    d.slab_k = kDftCols;
+    d.num_slabs = 3;
+    d.slab_row_shift[0] = 0;
+    d.slab_row_shift[1] = 0;
+    d.slab_row_shift[2] = kPlaneRows;
+    d.bias = nullptr;
+    d.act = WFL_ACT_NONE;
+    d.out_mode = WFL_OUT_STORE_F32;
+    d.alpha = 1.0f;
+    d.out = scratch_dft;
+    d.m_rows = kFrames;
+    d.out_row_stride = kDftCols;
+    d.out_batch_stride = static_cast<int64_t>(kFrames) * kDftCols;
+    d.tile_n = 128;
+    const int rc = wfl_gemm(&d, stream_);
+    if (rc != WFL_OK) return rc;
+  }
+  {
+    dim3 grid((kFrames + kFrameTile - 1) / kFrameTile, B);
+    logmel_post_kernel<<<grid, 256, kPostSmem, stream>>>(scratch_dft, mel_filters, n_mels, scratch_logspec,
+                                                         reinterpret_cast<unsigned*>(scratch_max));
+    WFL_CUDA(cudaGetLastError());
+  }
   const int64_t rows = static_cast<int64_t>(B) * kFrames;
   const int64_t total = rows * (out_stride / 2);
   const unsigned g2 = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16));

@@ -227,8 +227,7 @@ class Engine:
             ws["wave"] = torch.zeros(B, 480000, device=dev)
             ws["feats"] = torch.empty(B, 3000, MEL_PAD, **bf)
             ws["h1"] = torch.empty(B, 3000, d, **bf)
-            ws["logspec"] = torch.empty(B, 3000, self.arch["mels"], device=dev)
-            ws["smax"] = torch.empty(B, device=dev)
+            ws["mel_scratch"] = ops.logmel_scratch(B, self.arch["mels"], dev)
         elif n_samples is not None:
             Ts = self._wavlm_lengths(n_samples)
             large = self.arch["norm"] == "layer"
@@ -278,7 +277,7 @@ class Engine:
         if wave.dtype != torch.float32 or not wave.is_contiguous():
             wave = wave.float().contiguous()
         basis, filt = whisper_frontend_constants(a["mels"], self.dev)
-        ops.whisper_logmel(wave, n, basis, filt, a["mels"], ws["feats"], ws["logspec"], ws["smax"])
+        ops.whisper_logmel(wave, n, basis, filt, a["mels"], ws["feats"], ws["mel_scratch"])
         # conv1 (k3, p1) + GELU
         w1 = self.W["enc.conv1.w"]
         ops.gemm(ws["feats"], w1, ws["h1"], n=d, slab_k=MEL_PAD, shifts=[-1, 0, 1], cols=[0, 0, 0], a_rows=3000,

@@ -41,9 +41,22 @@ def mel_filters(n_mels, sr=16000, fmin=0.0, fmax=8000.0):
     return fb.astype(np.float32)
 
 
+def dft_basis_split():
+    """bf16 [448][3*448] = [W_hi | W_mid | W_hi]: the DFT basis transposed (row = output column, K = sample index,
+    zero padded 400 -> 448) and split hi + mid for the split-precision tensor-core contraction in csrc/logmel.cu."""
+    wt = torch.zeros(BASIS_COLS, BASIS_COLS)
+    wt[:, :N_FFT] = torch.from_numpy(dft_basis()).t()
+    hi = wt.to(torch.bfloat16)
+    mid = (wt - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, mid, hi], dim=1).contiguous()
+
+
+PLANE_SAMPLES = 3003 * HOP  # one padded-waveform plane of the strided view (csrc/logmel.cu kPlane)
+
+
 @functools.lru_cache(maxsize=None)
 def _constants_cpu(n_mels):
-    return torch.from_numpy(dft_basis()).contiguous(), torch.from_numpy(mel_filters(n_mels)).contiguous()
+    return dft_basis_split(), torch.from_numpy(mel_filters(n_mels)).contiguous()
 
 
 _DEVICE_CACHE = {}

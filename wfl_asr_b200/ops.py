@@ -131,12 +131,22 @@ def peak_normalize(samples_f64, clip_begin, n_clips, out, scratch_max, out_f64=N
     _count(2)
 
 
-def whisper_logmel(wave, n_samples, basis, filters, n_mels, out, scratch_logspec, scratch_max):
+def logmel_scratch(B, n_mels, device):
+    """Scratch buffers of wfl_whisper_logmel: (planes bf16, dft fp32 [B,3000,448], logspec fp32, clip max)."""
+    from .frontend import PLANE_SAMPLES
+    return (torch.empty(2 * PLANE_SAMPLES * B + 4096, dtype=torch.bfloat16, device=device),
+            torch.empty(B, 3000, 448, device=device), torch.empty(B, 3000, n_mels, device=device),
+            torch.empty(B, device=device))
+
+
+def whisper_logmel(wave, n_samples, basis_split, filters, n_mels, out, scratch):
     B = wave.shape[0]
-    rc = _lib.load().wfl_whisper_logmel(_ptr(wave), wave.stride(0), n_samples, B, _ptr(basis), _ptr(filters), n_mels,
-                                        _ptr(out), out.shape[-1], _ptr(scratch_logspec), _ptr(scratch_max), _stream())
+    planes, dft, logspec, smax = scratch
+    rc = _lib.load().wfl_whisper_logmel(_ptr(wave), wave.stride(0), n_samples, B, _ptr(basis_split), _ptr(filters), n_mels,
+                                        _ptr(out), out.shape[-1], _ptr(planes), _ptr(dft), _ptr(logspec), _ptr(smax),
+                                        _stream())
     _lib.check(rc, "wfl_whisper_logmel")
-    _count(2)
+    _count(4)
 
 
 def decode_frames(logits2d, L, o_id, threshold, ids):
