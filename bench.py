@@ -155,6 +155,9 @@ def run_ours(args, rank, world, local_rank):
         d[0] += 1
         d[1] += a.elapsed_time(b)
         d[2] += flops
+    if os.environ.get("WFL_BENCH_DEBUG"):
+        for tag, (n, tms, fl) in sorted(by_tag.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {tms / args.steps:7.3f} ms/step  x{n // args.steps:3d}  {fl / (tms * 1e-3) / 1e12:7.1f} TF  {tag}", file=sys.stderr)
     fam_ms = sum(v[1] for v in by_tag.values())
     fam_flops = sum(v[2] for v in by_tag.values())
     dom = max(by_tag.items(), key=lambda kv: kv[1][1]) if by_tag else None

@@ -67,9 +67,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint8_t* p_smem = kv_smem + KV_STAGES * Cfg::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * Cfg::kPBytes);
   uint64_t* q_full = bars;                      // [1]
-  uint64_t* kv_full = bars + 1;                 // [KV_STAGES]
-  uint64_t* kv_empty = kv_full + KV_STAGES;     // [KV_STAGES]
-  uint64_t* s_full = kv_empty + KV_STAGES;      // [2]
+  // K and V live in separate rings: K_j is dead as soon as S_j = Q K_j^T retired, V_j only after O += P_j V_j, so the
+  // next K tile streams in while softmax_j / PV_j are still running (one shared ring left the tensor pipe 75 % idle
+  // at hd 256: every QK_{j+1} waited for a TMA load that could only start after PV_{j-1}).
+  uint64_t* k_full = bars + 1;                  // [KV_STAGES]
+  uint64_t* k_empty = k_full + KV_STAGES;       // [KV_STAGES]
+  uint64_t* v_full = k_empty + KV_STAGES;       // [KV_STAGES]
+  uint64_t* v_empty = v_full + KV_STAGES;       // [KV_STAGES]
+  uint64_t* s_full = v_empty + KV_STAGES;       // [2]
   uint64_t* s_empty = s_full + 2;               // [2]
   uint64_t* p_full = s_empty + 2;               // [2]
   uint64_t* pv_done = p_full + 2;               // [2]
@@ -90,8 +95,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -116,14 +123,28 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* ks = kv_smem + stage * Cfg::kStageBytes;
-        uint8_t* vs = ks + Cfg::kKBytes;
-        mbar_expect_tx(&kv_full[stage], Cfg::kStageBytes);
-        for (int jb = 0; jb < Cfg::kHdBlocks; ++jb) {
-          tma_load_3d(ks + jb * (KV_TILE * 128), &map_kv, &kv_full[stage], p.k_col + h * HD + jb * 64, j * KV_TILE, b);
-          tma_load_3d(vs + jb * (KV_TILE * 128), &map_kv, &kv_full[stage], p.v_col + h * HD + jb * 64, j * KV_TILE, b);
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        uint8_t* ks = kv_smem + stage * Cfg::kKBytes;
+        mbar_expect_tx(&k_full[stage], Cfg::kKBytes);
+        for (int jb = 0; jb < Cfg::kHdBlocks; ++jb)
+          tma_load_3d(ks + jb * (KV_TILE * 128), &map_kv, &k_full[stage], p.k_col + h * HD + jb * 64, j * KV_TILE, b);
+        if (++stage == KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+    }
+  } else if (warp == 3) {
+    // ============================== TMA producer (V ring) ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        uint8_t* vs = kv_smem + KV_STAGES * Cfg::kKBytes + stage * Cfg::kVBytes;
+        mbar_expect_tx(&v_full[stage], Cfg::kVBytes);
+        for (int jb = 0; jb < Cfg::kHdBlocks; ++jb)
+          tma_load_3d(vs + jb * (KV_TILE * 128), &map_kv, &v_full[stage], p.v_col + h * HD + jb * 64, j * KV_TILE, b);
         if (++stage == KV_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -143,24 +164,26 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       auto issue_qk = [&](int j) {
         const int stage = j % KV_STAGES;
         const int sb = j & 1;
-        mbar_wait(&kv_full[stage], (j / KV_STAGES) & 1);
+        mbar_wait(&k_full[stage], (j / KV_STAGES) & 1);
         mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = kv_addr + stage * Cfg::kStageBytes;
+        const uint32_t k_addr = kv_addr + stage * Cfg::kKBytes;
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16) {
           const uint64_t da = umma_smem_desc(q_addr + (k16 >> 2) * (128 * 128) + (k16 & 3) * 32, 16, 1024);
           const uint64_t db = umma_smem_desc(k_addr + (k16 >> 2) * (KV_TILE * 128) + (k16 & 3) * 32, 16, 1024);
           umma_bf16_ss(tmem_base + sb * KV_TILE, da, db, idesc_qk, k16 > 0 ? 1u : 0u);
         }
+        umma_commit(&k_empty[stage]);  // K_j is dead once S_j retired: the next K tile may stream in now
         umma_commit(&s_full[sb]);
       };
       auto issue_pv = [&](int j) {
         const int stage = j % KV_STAGES;
         const int sb = j & 1;
+        mbar_wait(&v_full[stage], (j / KV_STAGES) & 1);
         mbar_wait(&p_full[sb], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = kv_addr + stage * Cfg::kStageBytes + Cfg::kKBytes;
+        const uint32_t v_addr = kv_addr + KV_STAGES * Cfg::kKBytes + stage * Cfg::kVBytes;
         const uint32_t pa = p_addr + sb * Cfg::kPBytes;
 #pragma unroll
         for (int nn = 0; nn < HD / kPvN; ++nn) {
@@ -175,20 +198,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             umma_bf16_ss(tmem_base + Cfg::kOCol + nn * kPvN, da, db, idesc_pv, (j > 0 || k16 > 0) ? 1u : 0u);
           }
         }
-        umma_commit(&kv_empty[stage]);
+        umma_commit(&v_empty[stage]);
         umma_commit(&pv_done[sb]);
       };
 
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < n_kv; ++j) {
-        if constexpr (KV_STAGES >= 2) {
-          if (j + 1 < n_kv) issue_qk(j + 1);
-          issue_pv(j);
-        } else {
-          issue_pv(j);
-          if (j + 1 < n_kv) issue_qk(j + 1);
-        }
+        if (j + 1 < n_kv) issue_qk(j + 1);  // S_{j+1} is computed while the softmax warps work on S_j
+        issue_pv(j);
       }
     }
   } else if (warp >= 4) {

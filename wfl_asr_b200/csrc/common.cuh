@@ -67,16 +67,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a descriptor/protocol bug must surface as a trap (reported as a CUDA error), never
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint
+// (ns) elapses, instead of returning after a few dozen cycles.  Without it the single-lane producer / MMA
+// waiters re-issue TRYWAIT+BRA continuously and steal issue slots from the math warps that share their SM
+// sub-partition (ncu: ~1/3 of all executed instructions in attention_kernel<64> were such spins).
+__device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_timeout_trap() {
+  printf("wfl: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+  __trap();
+}
+// Bounded wait: a descriptor/protocol bug must surface as a trap (reported as a CUDA error), never
 // as a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("wfl: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t tries = 0;
+  while (!mbar_try_wait_parked(bar, parity, 100000u)) {
+    if (++tries > (1u << 22)) mbar_timeout_trap();
   }
 }
 
