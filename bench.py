@@ -115,7 +115,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ops.TIMING = []
+    # live in the timed region: CUDA events around the dominant kernel only (the 31-tap conv GEMM, 4 launches/step)
+    ops.TIMING, ops.TIMING_MIN_SLABS = [], 16
     launches0 = ops.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -126,6 +127,13 @@ def run_ours(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     launches = ops.LAUNCHES - launches0
     timing, ops.TIMING = ops.TIMING, None
+    # separate, untimed pass: events around every GEMM launch for the family table (serialises launches slightly)
+    ops.TIMING, ops.TIMING_MIN_SLABS = [], 1
+    fam_steps = min(args.steps, 3)
+    for i in range(fam_steps):
+        step_resident(i)
+    torch.cuda.synchronize()
+    family, ops.TIMING = ops.TIMING, None
     # ---- timed region 2: end to end through the public call with HOST buffers (pinned H2D in, segments D2H out)
     for i in range(min(args.warmup, 2)):
         labeler.label_host(host_sets[i % len(host_sets)], lang)
@@ -149,17 +157,21 @@ def run_ours(args, rank, world, local_rank):
 
     peaks = measured_peaks()
     # dominant kernel: the Conformer conv-31 implicit GEMM (largest single launch); family totals reported too
-    by_tag = {}
-    for tag, flops, a, b in timing:
-        d = by_tag.setdefault(tag, [0, 0.0, 0.0])
-        d[0] += 1
-        d[1] += a.elapsed_time(b)
-        d[2] += flops
+    def tabulate(records):
+        table = {}
+        for tag, flops, a, b in records:
+            d = table.setdefault(tag, [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+            d[2] += flops
+        return table
+
+    by_tag, fam_tag = tabulate(timing), tabulate(family)
     if os.environ.get("WFL_BENCH_DEBUG"):
-        for tag, (n, tms, fl) in sorted(by_tag.items(), key=lambda kv: -kv[1][1]):
-            print(f"  {tms / args.steps:7.3f} ms/step  x{n // args.steps:3d}  {fl / (tms * 1e-3) / 1e12:7.1f} TF  {tag}", file=sys.stderr)
-    fam_ms = sum(v[1] for v in by_tag.values())
-    fam_flops = sum(v[2] for v in by_tag.values())
+        for tag, (n, tms, fl) in sorted(fam_tag.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {tms / fam_steps:7.3f} ms/step  x{n // fam_steps:3d}  {fl / (tms * 1e-3) / 1e12:7.1f} TF  {tag}", file=sys.stderr)
+    fam_ms = sum(v[1] for v in fam_tag.values()) * args.steps / fam_steps
+    fam_flops = sum(v[2] for v in fam_tag.values()) * args.steps / fam_steps
     dom = max(by_tag.items(), key=lambda kv: kv[1][1]) if by_tag else None
     roofline = None
     if dom is not None:
@@ -170,7 +182,9 @@ def run_ours(args, rank, world, local_rank):
                     "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
                     "launches": n, "avg_launch_ms": round(tms / n, 4),
                     "algorithmic_flop_per_launch": fl / n,
-                    "gemm_family": {"launches": sum(v[0] for v in by_tag.values()), "ms_per_step": round(fam_ms / args.steps, 3),
+                    "gemm_family": {"note": "all wfl_gemm launches, measured in a separate event-instrumented pass",
+                                    "launches_per_step": sum(v[0] for v in fam_tag.values()) // fam_steps,
+                                    "ms_per_step": round(fam_ms / args.steps, 3),
                                     "achieved": round(fam_flops / (fam_ms * 1e-3) / 1e12, 1),
                                     "share_of_step": round(fam_ms / ms, 3)}}
     value = audio_s_per_step * world * args.steps / (ms * 1e-3)

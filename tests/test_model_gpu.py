@@ -181,3 +181,38 @@ def test_infer_audio_end_to_end(tmp_path, seconds):
     print(f"[infer {seconds}s] {len(segs)} segments; frame-tag agreement with the fp32 oracle {n_agree / n_frames:.4%}")
     assert segs == expect
     assert n_agree / n_frames >= 0.97
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE configs[1] at full size (whisper-base, 6 encoder layers + 4 Conformer, batch 32 x 30 s): size-independent
+    properties -- run-to-run determinism (bitwise), batch invariance (clip i inside the batch == clip i alone, bitwise),
+    an fp32-oracle check on one clip of the batch, and .lab idempotence of the merge."""
+    from wfl_asr_b200 import synth
+    cfg = synth.workload_config("cfg2")
+    labels = synth.synth_labels(30)
+    model = synth.bench_model(BIOPhonemeTagger, cfg, labels)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    B = 32
+    clips = [synth.synth_wave(900 + i, 30.0 if i % 3 else 7.5 + 0.5 * i) for i in range(B)]  # mixed clip lengths
+    wave = torch.from_numpy(np.stack([np.pad(w, (0, 480000 - len(w))) for w in clips]).astype(np.float32))
+    lang = torch.tensor([i % 2 for i in range(B)], device=DEV)
+    l1, o1 = model(wave.to(DEV), lang)
+    l1, o1 = l1.clone(), o1.clone()
+    l2, o2 = model(wave.to(DEV), lang)
+    assert torch.equal(l1, l2) and torch.equal(o1, o2), "forward is not deterministic"
+    for i in (0, 13, 31):
+        li, oi = model(wave[i:i + 1].to(DEV), lang[i:i + 1])
+        assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch 32 and batch 1"
+    ref_l, ref_o = to.forward(wave[13:14], sd, cfg, lang[13:14].cpu())
+    rel, agree, agree_safe, off_err = _compare("cfg2 full size, clip 13", l1[13:14].float().cpu(), o1[13:14].float().cpu(), ref_l, ref_o)
+    assert rel <= 1e-2 and agree_safe == 1.0
+    lab = Labeler(model, median_filter=5, merge_mode="right", confidence_threshold=0.5)
+    ids, merged, nout, fcb, n_files = lab.postprocess(l1, o1)
+    segs = lab.fetch(merged, nout, fcb, n_files, 1500)
+    assert sum(len(s) for s in segs) > 0
+    for b in (0, 13):
+        want = po.merge_adjacent_segments(po.decode_bio_tags([labels[k] for k in ids[b].cpu().numpy()], 0.02,
+                                                             o1[b].float().cpu().numpy()), "right")
+        assert segs[b] == want
+        assert po.merge_adjacent_segments(list(segs[b]), "right") == segs[b]  # merging is idempotent

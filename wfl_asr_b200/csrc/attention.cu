@@ -21,6 +21,10 @@
 
 namespace wfl {
 
+int attention_big_dispatch(const void* qkv, int64_t row_stride, int64_t batch_stride, int q_col, int k_col, int v_col,
+                           int B, int T, int H, int hd, float scale, void* out, int64_t out_row_stride,
+                           int64_t out_batch_stride, cudaStream_t stream);  // attention_big.cu
+
 constexpr int kAttnThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
@@ -109,10 +113,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
@@ -413,8 +419,7 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
     configured = true;
   }
   dim3 grid((T + 127) / 128, H, B);
-  kern<<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(mq, mkv, mo, p);
-  WFL_CUDA(cudaGetLastError());
+  WFL_CUDA(launch_pdl(kern, grid, dim3(kAttnThreads), Cfg::kSmemBytes, stream, mq, mkv, mo, p));
   return WFL_OK;
 }
 
@@ -454,7 +459,12 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
       return launch_attention<384, 64, 1>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                           out_batch_stride, stream);
     default:
-      set_error("wfl_attention: head_dim %d not built yet (supported: 64, 256, 384)", hd);
-      return WFL_ERR_UNSUPPORTED;
+      if (rel_bias != nullptr) {
+        set_error("wfl_attention: relative-position bias is only built for head_dim 64/256/384 (got %d)", hd);
+        return WFL_ERR_UNSUPPORTED;
+      }
+      // head_dim 512 / 640: streamed-Q, split-V variant (attention_big.cu)
+      return attention_big_dispatch(qkv, row_stride, batch_stride, q_col, k_col, v_col, B, T, H, hd, scale, out,
+                                    out_row_stride, out_batch_stride, stream);
   }
 }

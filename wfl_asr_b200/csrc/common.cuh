@@ -38,6 +38,29 @@ int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const
                     CUtensorMapSwizzle swizzle);
 
 #ifdef __CUDACC__
+// ------------------------------------------------------------------------------------- programmatic dependent launch
+// Kernels that call pdl_wait() before their first global-memory access are launched with the
+// programmatic-stream-serialization attribute: their prologue (barrier init, TMEM alloc, tensor-map prefetch)
+// overlaps the tail of the previous kernel in the stream; pdl_launch_dependents() lets the next one do the same.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------- device PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -18,7 +18,6 @@
 
 namespace wfl {
 
-constexpr int kLstmCluster = 8;
 constexpr int kLstmNB = 8;  // batch items per cluster = one n8 MMA tile
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -47,9 +46,11 @@ __device__ __forceinline__ float tanh_acc(float x) {
   return 1.0f - 2.0f / (1.0f + e);
 }
 
-template <int H>
+// CL = CTAs per cluster: 8 (portable) up to H = 384; 16 (non-portable, opt-in) for H = 512 / 640 so that each CTA's
+// W_hh slice (4 * H/CL rows x H) still fits the register file as MMA fragments.
+template <int H, int CL>
 struct LstmCfg {
-  static constexpr int kUnits = H / kLstmCluster;   // hidden units per CTA
+  static constexpr int kUnits = H / CL;             // hidden units per CTA
   static constexpr int kGroups = kUnits / 8;        // 8-unit groups, one (pair of) warp(s) each
   static constexpr int kKSplit = 2;
   static constexpr int kWarps = kGroups * kKSplit;
@@ -60,15 +61,16 @@ struct LstmCfg {
   static constexpr int kStageBytes = kLstmNB * kUnits * 2;  // this CTA's h slice, [n][unit] bf16
   static constexpr int kPartBytes = kGroups * 32 * 8 * 4;   // K-half partial sums
   static constexpr int kVecPerRow = kUnits * 2 / 16;        // 16-byte vectors per (n) row of the slice
-  static_assert(H % (kLstmCluster * 8) == 0, "H must be a multiple of 64");
+  static_assert(H % (CL * 8) == 0, "H must be a multiple of 8 * cluster size");
   static_assert((kUnits * 2) % 16 == 0, "slice rows must be 16-byte multiples");
 };
 
-template <int H>
-__global__ void __launch_bounds__(LstmCfg<H>::kThreads, 1)
+template <int H, int CL>
+__global__ void __launch_bounds__((LstmCfg<H, CL>::kThreads), 1)
 lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh, int B, int T,
             __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32) {
-  using Cfg = LstmCfg<H>;
+  using Cfg = LstmCfg<H, CL>;
+  constexpr int kLstmCluster = CL;
   __shared__ __align__(16) uint8_t hbuf_raw[Cfg::kHBufBytes];
   __shared__ __align__(16) uint8_t stage_raw[Cfg::kStageBytes];
   __shared__ __align__(16) float part[Cfg::kGroups * 32 * 8];
@@ -199,9 +201,17 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
   }
 }
 
-template <int H>
+template <int H, int CL>
 static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_bf16, float* y_f32, cudaStream_t stream) {
-  using Cfg = LstmCfg<H>;
+  using Cfg = LstmCfg<H, CL>;
+  constexpr int kLstmCluster = CL;
+  if (CL > 8) {
+    static bool allowed = false;
+    if (!allowed) {
+      WFL_CUDA(cudaFuncSetAttribute(lstm_kernel<H, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      allowed = true;
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kLstmCluster, (B + kLstmNB - 1) / kLstmNB, 2);
   cfg.blockDim = dim3(Cfg::kThreads);
@@ -214,7 +224,7 @@ static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_b
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  WFL_CUDA(cudaLaunchKernelEx(&cfg, lstm_kernel<H>, gx, static_cast<const __nv_bfloat16*>(whh), B, T,
+  WFL_CUDA(cudaLaunchKernelEx(&cfg, lstm_kernel<H, CL>, gx, static_cast<const __nv_bfloat16*>(whh), B, T,
                               static_cast<__nv_bfloat16*>(y_bf16), y_f32));
   return WFL_OK;
 }
@@ -228,11 +238,13 @@ extern "C" int wfl_lstm_layer(const float* gx, const void* whh_bf16, int32_t B, 
   WFL_CHECK_ARG(gx && whh_bf16 && (y_bf16 || y_f32), "wfl_lstm_layer: null pointer");
   WFL_CHECK_ARG(B >= 1 && T >= 1, "wfl_lstm_layer: empty problem");
   switch (H) {
-    case 192: return launch_lstm<192>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
-    case 256: return launch_lstm<256>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
-    case 384: return launch_lstm<384>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 192: return launch_lstm<192, 8>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 256: return launch_lstm<256, 8>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 384: return launch_lstm<384, 8>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 512: return launch_lstm<512, 16>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 640: return launch_lstm<640, 16>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
     default:
-      set_error("wfl_lstm_layer: hidden size %d not built yet (supported: 192, 256, 384)", H);
+      set_error("wfl_lstm_layer: hidden size %d not built (supported: 192, 256, 384, 512, 640)", H);
       return WFL_ERR_UNSUPPORTED;
   }
 }

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta2, float eps,
                                                         float* __restrict__ out_f32,
                                                         __nv_bfloat16* __restrict__ out_bf16, int act) {
+  pdl_launch_dependents();  // the GEMM that consumes this output may run its prologue while these rows finish
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;

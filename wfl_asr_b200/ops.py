@@ -10,7 +10,9 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, MERGE_MODES, OUT_ADD_F32, OUT_G
                    OUT_STORE_F32, GemmDesc, Segment, WflError)
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
-TIMING = None  # bench.py sets this to a list: every GEMM launch appends (tag, algorithmic flops, start, end events)
+TIMING = None  # bench.py sets this to a list: timed GEMM launches append (tag, algorithmic flops, start, end events)
+TIMING_MIN_SLABS = 1  # only launches with at least this many K-slabs are bracketed by events (event records between
+#                       kernels defeat programmatic dependent launch, so the timed region brackets the dominant kernel only)
 
 
 def _count(n=1):
@@ -53,11 +55,12 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
     d.tile_n = tile_n
     if not (a.is_cuda and w.is_cuda and out.is_cuda):
         raise WflError("wfl_gemm needs CUDA tensors (no CPU fallback exists)")
-    if TIMING is not None:
+    timed = TIMING is not None and len(shifts) >= TIMING_MIN_SLABS
+    if timed:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(_lib.load().wfl_gemm(ctypes.byref(d), _stream()), "wfl_gemm")
-    if TIMING is not None:
+    if timed:
         e1.record()
         tag = f"M{batches * d.m_rows}xN{n}xK{len(shifts) * slab_k}/slabs{len(shifts)}/mode{out_mode}"
         TIMING.append((tag, 2.0 * batches * d.m_rows * n * len(shifts) * slab_k, e0, e1))
