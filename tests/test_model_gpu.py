@@ -127,6 +127,17 @@ def test_utils_dropins_match_oracle(golden):
         utils.merge_adjacent_segments([(0.0, 1.0, "a")], "sideways")
 
 
+def test_label_stream_matches_synchronous_label():
+    """The pipelined host-buffer API (copy stream + double buffering) returns exactly what the synchronous call does."""
+    cfg, labels, sd, wave, lang, model = _build("whisper_base_cfg2")
+    lab = Labeler(model, median_filter=3, merge_mode="right", confidence_threshold=0.0)
+    batches = [torch.cat([wave, wave.flip(1) * s], 0).pin_memory() for s in (0.9, 0.5, 0.7)]
+    lang2 = torch.tensor([0, 1], device=DEV)
+    want = [lab.label(b.to(DEV), lang2) for b in batches]
+    got = list(lab.label_stream(iter(batches), lang2))
+    assert got == want and sum(len(s) for batch in got for s in batch) > 0
+
+
 def _write_wav(path, x, sr=16000):
     pcm = (np.clip(x, -1, 1) * 32767.0).astype("<i2").tobytes()
     with open(path, "wb") as f:

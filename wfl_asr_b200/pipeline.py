@@ -116,15 +116,79 @@ class Labeler:
         wave = wave_host.to(self.dev, non_blocking=True)
         return self.label(wave, lang_id)
 
+    @torch.no_grad()
+    def label_stream(self, host_batches, lang_id=None):
+        """Pipelined end-to-end labeling of a sequence of HOST batches (pinned fp32 [B, N] tensors of one shape):
+        yields, per batch, the list (per clip) of [(start, end, phoneme)].  The H2D copy of batch i+1 runs on a copy
+        stream while batch i computes, and the D2H of batch i's segment records is decoded on the host while batch
+        i+1 computes -- every byte still crosses PCIe, it just no longer serialises with the kernels."""
+        dev = self.dev
+        main = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        it = iter(host_batches)
+        slots = [None, None]  # device staging (double buffered)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(slot):
+            try:
+                host = next(it)
+            except StopIteration:
+                return None
+            reuse = slots[slot] is not None and slots[slot].shape == host.shape
+            if not reuse:  # allocated on the main stream's pool; the copy stream only ever writes into it
+                slots[slot] = torch.empty(host.shape, dtype=torch.float32, device=dev)
+                copy.wait_stream(main)
+            with torch.cuda.stream(copy):
+                if reuse:
+                    copy.wait_event(freed[slot])  # the forward that last read this staging buffer has finished
+                slots[slot].copy_(host, non_blocking=True)
+                ready[slot].record(copy)
+            return slot
+
+        host_rec, host_cnt = [None, None], [None, None]  # pinned result buffers, alternating
+        pending = None  # (slot, done event, T, n_files) of the batch whose results are still in flight
+        cur = prefetch(0)
+        i = 0
+        while cur is not None:
+            nxt = prefetch((i + 1) & 1)
+            main.wait_event(ready[cur])
+            logits, offsets = self.model(slots[cur], lang_id)
+            freed[cur].record(main)
+            _, merged, nout, fcb, n_files = self.postprocess(logits, offsets)
+            k = i & 1
+            if host_rec[k] is None or host_rec[k].shape != merged.shape:
+                host_rec[k] = torch.empty(merged.shape, dtype=torch.uint8).pin_memory()
+                host_cnt[k] = torch.empty(nout.shape, dtype=torch.int32).pin_memory()
+            host_rec[k].copy_(merged, non_blocking=True)
+            host_cnt[k].copy_(nout, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:  # decode the previous batch on the host while this one runs on the GPU
+                yield self._decode_host(host_rec, host_cnt, *pending)
+            pending = (k, done, logits.shape[1], n_files)
+            cur = nxt
+            i += 1
+        if pending is not None:
+            yield self._decode_host(host_rec, host_cnt, *pending)
+
+    def _decode_host(self, host_rec, host_cnt, k, done, T, n_files):
+        done.synchronize()
+        return self._to_python(host_rec[k].numpy().reshape(-1).view(SEG_DTYPE), host_cnt[k].numpy(),
+                               np.arange(n_files + 1), n_files, T)
+
+    def _to_python(self, raw, counts, begins, n_files, stride):
+        names = self.out_names
+        out = []
+        for f in range(n_files):
+            base = int(begins[f]) * stride
+            rec = raw[base:base + int(counts[f])]
+            out.append(list(zip(rec["start"].tolist(), rec["end"].tolist(), [names[p] for p in rec["ph"].tolist()])))
+        return out
+
     def fetch(self, merged, nout, file_clip_begin, n_files, stride):
         """One D2H copy of the segment records (+ counts); returns python tuples like the reference."""
         counts = nout[:n_files].cpu().numpy()
         begins = file_clip_begin.cpu().numpy()
         raw = merged.cpu().numpy().reshape(-1).view(SEG_DTYPE)
-        out = []
-        for f in range(n_files):
-            base = int(begins[f]) * stride
-            rec = raw[base:base + int(counts[f])]
-            names = self.out_names
-            out.append([(float(s), float(e), names[int(p)]) for s, e, p in zip(rec["start"], rec["end"], rec["ph"])])
-        return out
+        return self._to_python(raw, counts, begins, n_files, stride)
