@@ -77,7 +77,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("WFL_LIB") or _build.LIB_PATH  # WFL_LIB: an experiment build of the same sources (tools/)
     if not os.path.exists(path):
         _build.build()
     try:

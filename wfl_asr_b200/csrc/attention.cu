@@ -2,15 +2,20 @@
 //
 //   out[b, t, h*HD:(h+1)*HD] = softmax_k(scale * q.k + gate[b,h,t] * rel_bias[h, k - t + T - 1]) v
 //
-// One CTA per (128-query tile, head, batch item).  Warp roles: warp 0 = TMA producer (Q once, then a ring
-// of K/V tiles), warp 1 = one elected thread issuing tcgen05.mma, warp 2 = TMEM allocator, warps 4-7 =
-// softmax: thread r owns query row r (TMEM lane r), so row max / row sum need no shuffles.
+// One CTA per (128-query tile, head, batch item), 12 warps:
+//   warp 0  TMA producer: Q once, then the K ring          warp 3  TMA producer: V ring
+//   warp 1  one elected thread issuing tcgen05.mma         warp 2  TMEM allocator
+//   warps 4-11  softmax / correction / epilogue.  Query row r lives in TMEM lane r; the two warps that share a
+//               lane quarter split the 64 score columns of a tile (32 each), so 8 softmax warps per CTA keep
+//               4 warps per SM sub-partition busy at 2 CTAs/SM (the single-warp-per-row version was latency bound).
 //   S_j = Q K_j^T           -> TMEM (fp32, double-buffered so S_{j+1} is computed while softmax_j runs)
 //   P_j = 2^(S_j*c - m)     -> bf16, written by the softmax threads into 128B-swizzled smem (A operand)
 //   O  += P_j V_j           -> TMEM (fp32, HD columns); V is consumed MN-major straight from its TMA tile.
+// K and V stream through separate TMA rings: K_j is dead once S_j retired, V_j only after O += P_j V_j.
 // Online softmax with lazy rescaling: O and the row sum are rescaled only when the running max grows
 // by more than 2^8, so the TMEM read-modify-write of O is rare.
-// Head sizes: 64 (Whisper/WavLM encoders), 256 and 384 (Conformer heads=2 at d=512/768; REF/config.yaml:28).
+// Head sizes: 64 (Whisper/WavLM encoders, 2 CTAs/SM), 256 and 384 (Conformer heads=2 at d=512/768;
+// REF/config.yaml:28); 512/640 are handled by attention_big.cu.
 //
 // Reference arithmetic replaced: TF/models/whisper/modeling_whisper.py:284-357 (SDPA, q pre-scaled),
 // nn.MultiheadAttention at REF/model.py:26,42 (TORCH/nn/functional.py multi_head_attention_forward),
@@ -25,30 +30,47 @@ int attention_big_dispatch(const void* qkv, int64_t row_stride, int64_t batch_st
                            int B, int T, int H, int hd, float scale, void* out, int64_t out_row_stride,
                            int64_t out_batch_stride, cudaStream_t stream);  // attention_big.cu
 
-constexpr int kAttnThreads = 256;
+// P (the bf16 probabilities) is handed to the tensor core through TMEM, overlaying the S tile it was computed from
+// (tcgen05.st by the softmax warps, A-from-TMEM MMA).  At hd 64 the kernel was shared-memory-bandwidth bound: per
+// 64-key tile the MMAs read Q 16 KB + K 8 KB + P 16 KB + V 8 KB and the softmax wrote P 16 KB; this removes 32 KB.
+// false = stage P in 128B-swizzled shared memory (A-from-smem MMA).
+constexpr bool kPTmem = true;
+constexpr int kAttnThreads = 384;
+constexpr int kKvTile = 64;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef WFL_EXP_NOEXP  // experiment build only (tools/build_variant.py): take MUFU out to see what bounds the kernel
+  return fmaf(x, 1e-3f, 1.0f);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
+}
+// barrier shared by the two softmax warps of one TMEM lane quarter (ids 2..5; 0 = __syncthreads)
+__device__ __forceinline__ void pair_sync(int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 2) : "memory");
 }
 
-template <int HD, int KV_TILE, int KV_STAGES>
+template <int HD, int KV_STAGES>
 struct AttnCfg {
   static constexpr int kHdBlocks = HD / 64;
   static constexpr int kQBytes = 128 * HD * 2;
-  static constexpr int kKBytes = KV_TILE * HD * 2;
-  static constexpr int kVBytes = KV_TILE * HD * 2;
-  static constexpr int kStageBytes = kKBytes + kVBytes;
-  static constexpr int kPBlocks = KV_TILE / 64;
-  static constexpr int kPBytes = 128 * KV_TILE * 2;
-  static constexpr int kSmemBytes = kQBytes + KV_STAGES * kStageBytes + 2 * kPBytes + 256 + 1024;
-  static constexpr int kOCol = 2 * KV_TILE;  // TMEM column where O starts (after two S buffers)
+  static constexpr int kKBytes = kKvTile * HD * 2;
+  static constexpr int kVBytes = kKvTile * HD * 2;
+  static constexpr int kPBytes = kPTmem ? 0 : 128 * kKvTile * 2;
+  static constexpr int kXchgBytes = 2 * 2 * 128 * 4;  // row-max exchange, double-buffered (row sums reuse the idle half)
+  static constexpr int kSmemBytes = kQBytes + KV_STAGES * (kKBytes + kVBytes) + 2 * kPBytes + kXchgBytes + 256;
+  // S is triple-buffered when TMEM allows: the single MMA-issuing thread is in-order, so with two buffers QK_{j+2}
+  // could only be issued after P_j arrived; a third buffer lets it run two tiles ahead of the softmax warps.
+  static constexpr int kSBufs = HD <= 256 ? 3 : 2;
+  static constexpr int kOCol = kSBufs * kKvTile;  // TMEM column where O starts (after the S buffers)
   static_assert(kOCol + HD <= 512, "TMEM overflow");
   static constexpr uint32_t kTmemCols = kOCol + HD <= 256 ? 256 : 512;
   static constexpr int kCtasPerSm = (kSmemBytes <= 113 * 1024 && kTmemCols <= 256) ? 2 : 1;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 struct AttnParams {
@@ -59,28 +81,33 @@ struct AttnParams {
   const float* gate;      // [B][H][T] or null
 };
 
-template <int HD, int KV_TILE, int KV_STAGES>
-__global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_TILE, KV_STAGES>::kCtasPerSm))
+template <int HD, int KV_STAGES>
+__global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES>::kCtasPerSm))
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                  const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
-  using Cfg = AttnCfg<HD, KV_TILE, KV_STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Cfg = AttnCfg<HD, KV_STAGES>;
+  constexpr int KV_TILE = kKvTile;
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (128B swizzle); checked below
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("wfl_attention: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* q_smem = smem;
-  uint8_t* kv_smem = q_smem + Cfg::kQBytes;
-  uint8_t* p_smem = kv_smem + KV_STAGES * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p_smem + 2 * Cfg::kPBytes);
+  uint8_t* k_smem = q_smem + Cfg::kQBytes;
+  uint8_t* v_smem = k_smem + KV_STAGES * Cfg::kKBytes;
+  uint8_t* p_smem = v_smem + KV_STAGES * Cfg::kVBytes;
+  float* xmax = reinterpret_cast<float*>(p_smem + 2 * Cfg::kPBytes);  // [2 (tile parity)][2 (column half)][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xmax + 2 * 2 * 128);
   uint64_t* q_full = bars;                      // [1]
-  // K and V live in separate rings: K_j is dead as soon as S_j = Q K_j^T retired, V_j only after O += P_j V_j, so the
-  // next K tile streams in while softmax_j / PV_j are still running (one shared ring left the tensor pipe 75 % idle
-  // at hd 256: every QK_{j+1} waited for a TMA load that could only start after PV_{j-1}).
   uint64_t* k_full = bars + 1;                  // [KV_STAGES]
   uint64_t* k_empty = k_full + KV_STAGES;       // [KV_STAGES]
   uint64_t* v_full = k_empty + KV_STAGES;       // [KV_STAGES]
   uint64_t* v_empty = v_full + KV_STAGES;       // [KV_STAGES]
-  uint64_t* s_full = v_empty + KV_STAGES;       // [2]
-  uint64_t* s_empty = s_full + 2;               // [2]
-  uint64_t* p_full = s_empty + 2;               // [2]
+  constexpr int S_BUFS = Cfg::kSBufs;
+  uint64_t* s_full = v_empty + KV_STAGES;       // [S_BUFS]
+  uint64_t* s_empty = s_full + S_BUFS;          // [S_BUFS]
+  uint64_t* p_full = s_empty + S_BUFS;          // [2]
   uint64_t* pv_done = p_full + 2;               // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
@@ -104,10 +131,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < S_BUFS; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], kPTmem ? 1 : 8);  // P overlays S in TMEM: the buffer is free only once PV_j retired
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 8);
       mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
@@ -121,7 +150,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   pdl_wait();
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
+    // ============================== TMA producer: Q, K ring ==============================
     if (lane == 0) {
       mbar_expect_tx(q_full, Cfg::kQBytes);
       for (int jb = 0; jb < Cfg::kHdBlocks; ++jb)
@@ -130,7 +159,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&k_empty[stage], phase ^ 1);
-        uint8_t* ks = kv_smem + stage * Cfg::kKBytes;
+        uint8_t* ks = k_smem + stage * Cfg::kKBytes;
         mbar_expect_tx(&k_full[stage], Cfg::kKBytes);
         for (int jb = 0; jb < Cfg::kHdBlocks; ++jb)
           tma_load_3d(ks + jb * (KV_TILE * 128), &map_kv, &k_full[stage], p.k_col + h * HD + jb * 64, j * KV_TILE, b);
@@ -141,13 +170,13 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
   } else if (warp == 3) {
-    // ============================== TMA producer (V ring) ==============================
+    // ============================== TMA producer: V ring ==============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
         mbar_wait(&v_empty[stage], phase ^ 1);
-        uint8_t* vs = kv_smem + KV_STAGES * Cfg::kKBytes + stage * Cfg::kVBytes;
+        uint8_t* vs = v_smem + stage * Cfg::kVBytes;
         mbar_expect_tx(&v_full[stage], Cfg::kVBytes);
         for (int jb = 0; jb < Cfg::kHdBlocks; ++jb)
           tma_load_3d(vs + jb * (KV_TILE * 128), &map_kv, &v_full[stage], p.v_col + h * HD + jb * 64, j * KV_TILE, b);
@@ -157,23 +186,29 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1 || warp == 2) {
+    // ============================== MMA issuers ==============================
+    // Two issuing threads: warp 1 issues every S_j = Q K_j^T, warp 2 every O += P_j V_j.  A per-tile timeline trace
+    // showed ONE thread needing ~2000 cycles per 64-key tile for 8 tcgen05.mma + 5 commits + 4 barrier waits --
+    // the whole kernel was paced by it, not by MUFU, shared memory or the tensor pipe.  All ordering between the two
+    // streams of MMAs already goes through mbarriers (s_full/s_empty, p_full, pv_done).
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, KV_TILE, 0, 0);
-      constexpr int kPvN = HD <= 256 ? HD : HD / 2;  // N per PV instruction (<= 256)
+      constexpr int kPvN = HD <= 256 ? HD : HD / 2;  // N per PV instruction (<= 256, whole 64-column boxes)
+      static_assert(kPvN % 64 == 0, "PV chunks must be whole 64-column boxes");
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kPvN, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(q_smem);
-      const uint32_t kv_addr = smem_u32(kv_smem);
+      const uint32_t k_addr0 = smem_u32(k_smem);
+      const uint32_t v_addr0 = smem_u32(v_smem);
       const uint32_t p_addr = smem_u32(p_smem);
 
       auto issue_qk = [&](int j) {
         const int stage = j % KV_STAGES;
-        const int sb = j & 1;
+        const int sb = j % S_BUFS;
         mbar_wait(&k_full[stage], (j / KV_STAGES) & 1);
-        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+        mbar_wait(&s_empty[sb], ((j / S_BUFS) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = kv_addr + stage * Cfg::kKBytes;
+        const uint32_t k_addr = k_addr0 + stage * Cfg::kKBytes;
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16) {
           const uint64_t da = umma_smem_desc(q_addr + (k16 >> 2) * (128 * 128) + (k16 & 3) * 32, 16, 1024);
@@ -189,36 +224,44 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         mbar_wait(&v_full[stage], (j / KV_STAGES) & 1);
         mbar_wait(&p_full[sb], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = kv_addr + KV_STAGES * Cfg::kKBytes + stage * Cfg::kVBytes;
+        const uint32_t v_addr = v_addr0 + stage * Cfg::kVBytes;
         const uint32_t pa = p_addr + sb * Cfg::kPBytes;
+        const int ss = j % S_BUFS;
 #pragma unroll
         for (int nn = 0; nn < HD / kPvN; ++nn) {
 #pragma unroll
           for (int k16 = 0; k16 < KV_TILE / 16; ++k16) {
-            // A = P: K-major, 64-column blocks of [128 x 128 B]
-            const uint64_t da = umma_smem_desc(pa + (k16 >> 2) * (128 * 128) + (k16 & 3) * 32, 16, 1024);
             // B = V: MN-major. 64 hd-columns contiguous (128 B), 8 kv rows = one 1024 B atom (SBO),
-            // next 64 hd-columns one block (KV_TILE*128 B) further (LBO).
+            // next 64 hd-columns one box (KV_TILE*128 B) further (LBO).
             const uint64_t db = umma_smem_desc(v_addr + nn * (kPvN / 64) * (KV_TILE * 128) + k16 * 2048,
                                                KV_TILE * 128, 1024);
-            umma_bf16_ss(tmem_base + Cfg::kOCol + nn * kPvN, da, db, idesc_pv, (j > 0 || k16 > 0) ? 1u : 0u);
+            const uint32_t acc = (j > 0 || k16 > 0) ? 1u : 0u;
+            if constexpr (kPTmem) {
+              // A = P from TMEM: 16 keys = 8 packed 32-bit columns per instruction, overlaying S buffer ss
+              umma_bf16_ts(tmem_base + Cfg::kOCol + nn * kPvN, tmem_base + ss * KV_TILE + k16 * 8, db, idesc_pv, acc);
+            } else {
+              const uint64_t da = umma_smem_desc(pa + k16 * 32, 16, 1024);  // A = P: K-major [128 x 128 B]
+              umma_bf16_ss(tmem_base + Cfg::kOCol + nn * kPvN, da, db, idesc_pv, acc);
+            }
           }
         }
         umma_commit(&v_empty[stage]);
+        if constexpr (kPTmem) umma_commit(&s_empty[ss]);
         umma_commit(&pv_done[sb]);
       };
 
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_qk(j + 1);  // S_{j+1} is computed while the softmax warps work on S_j
-        issue_pv(j);
+      if (warp == 1) {
+        mbar_wait(q_full, 0);
+        for (int j = 0; j < n_kv; ++j) issue_qk(j);  // runs up to S_BUFS tiles ahead of the softmax warps
+      } else {
+        for (int j = 0; j < n_kv; ++j) issue_pv(j);
       }
     }
   } else if (warp >= 4) {
     // ============================== softmax / correction / epilogue ==============================
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const int quarter = warp & 3;          // TMEM lane quarter
+    const int ch = (warp - 4) >> 2;        // which 32 of the tile's 64 score columns / which half of O's columns
+    const int r = quarter * 32 + lane;     // query row inside the tile == TMEM lane
     const int q_idx = q0 + r;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const bool has_bias = p.rel_bias != nullptr;
@@ -230,105 +273,118 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       bias_row = p.rel_bias + static_cast<int64_t>(h) * (2 * p.T - 1) + (p.T - 1 - qi);  // + k
     }
     float m_used = -INFINITY;
-    float l_sum = 0.f;
+    float l_sum = 0.f;  // this warp's 32 columns only; the two halves are added in the epilogue
+    constexpr int kOHalf = HD / 2;
 
     for (int j = 0; j < n_kv; ++j) {
-      const int sb = j & 1;
-      const int kv0 = j * KV_TILE;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      const int sb = j & 1;         // P / exchange buffer parity
+      const int ss = j % S_BUFS;    // S buffer
+      const int kv0 = j * KV_TILE + ch * 32;  // first key of this warp's columns
+      mbar_wait(&s_full[ss], (j / S_BUFS) & 1);
       tc_fence_after();
-      const uint32_t s_addr = lane_addr + sb * KV_TILE;
+#ifndef WFL_EXP_NOSOFTMAX  // experiment build only: skip the math, keep the barrier protocol
+      uint32_t v[32];
+      tmem_ld32(lane_addr + ss * KV_TILE + ch * 32, v);
+      tmem_ld_wait();
 
       // One tile of online softmax, specialised on (relative-position bias, partial last tile) so the common
-      // case costs ~1 FMNMX (pass 1) and FFMA + MUFU.EX2 + FADD + half a CVT (pass 2) per score.
+      // case costs one FMNMX, then FFMA + MUFU.EX2 + FADD + half a CVT per score.
       auto tile = [&](auto bias_c, auto tail_c) {
         constexpr bool kBias = decltype(bias_c)::value;
         constexpr bool kTail = decltype(tail_c)::value;
-        // x(v, k): score in log2 units
-        auto score = [&](uint32_t raw, int k) -> float {
-          float x = __uint_as_float(raw) * p.scale_log2;
-          if constexpr (kBias) {
-            if (!kTail || k < p.T) x = fmaf(gate_l2, __ldg(bias_row + k), x);
-          }
-          if constexpr (kTail) x = k < p.T ? x : -INFINITY;
-          return x;
-        };
-        // pass 1: row max
+        float x[32];  // scores in log2 units (general path only)
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < KV_TILE; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(s_addr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if constexpr (!kBias && !kTail)
-              mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(v[i]));  // scale > 0: max commutes with the scaling
-            else
-              mx[i & 3] = fmaxf(mx[i & 3], score(v[i], kv0 + c + i));
+        for (int i = 0; i < 32; ++i) {
+          if constexpr (!kBias && !kTail) {
+            mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(v[i]));  // scale > 0: max commutes with the scaling
+          } else {
+            const int k = kv0 + i;
+            float s = __uint_as_float(v[i]) * p.scale_log2;
+            if constexpr (kBias) {
+              if (!kTail || k < p.T) s = fmaf(gate_l2, __ldg(bias_row + k), s);
+            }
+            if constexpr (kTail) s = k < p.T ? s : -INFINITY;
+            x[i] = s;
+            mx[i & 3] = fmaxf(mx[i & 3], s);
           }
         }
-        float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        if constexpr (!kBias && !kTail) m_tile *= p.scale_log2;
+        float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if constexpr (!kBias && !kTail) m_half *= p.scale_log2;
+        // combine with the warp that owns the other 32 columns of these rows
+        float* xm = xmax + (sb * 2) * 128;
+        xm[ch * 128 + r] = m_half;
+        pair_sync(quarter);
+        const float m_tile = fmaxf(m_half, xm[(ch ^ 1) * 128 + r]);
         const float m_new = fmaxf(m_used, m_tile);
         const bool grow = m_new > m_used + kRescaleThreshold;  // also true on the first tile (m_used = -inf)
-        if (__any_sync(0xffffffffu, grow)) {
+        if (__any_sync(0xffffffffu, grow)) {                   // identical decision in both warps of the pair
           if (j > 0) {
-            // O holds sum_{i<j} P_i V_i scaled by 2^-m_used: rescale it (all rows of this warp) once PV(j-1) retired
+            // O holds sum_{i<j} P_i V_i scaled by 2^-m_used: rescale this warp's half of its columns once PV(j-1) retired
             mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
             tc_fence_after();
             const float factor = ex2_approx(m_used - m_new);
 #pragma unroll 1
-            for (int c = 0; c < HD; c += 32) {
+            for (int c = 0; c < kOHalf; c += 32) {
               uint32_t o[32];
-              tmem_ld32(lane_addr + Cfg::kOCol + c, o);
+              tmem_ld32(lane_addr + Cfg::kOCol + ch * kOHalf + c, o);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-              tmem_st32(lane_addr + Cfg::kOCol + c, o);
+              tmem_st32(lane_addr + Cfg::kOCol + ch * kOHalf + c, o);
             }
             tmem_st_wait();
             l_sum *= factor;
           }
           m_used = m_new;
         }
-        // the P buffer we are about to overwrite was read by PV(j-2)
-        if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
+        if constexpr (!kPTmem) {
+          // the smem P buffer we are about to overwrite was read by PV(j-2)
+          if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
+        }
 
-        // pass 2: P = 2^(x - m_used) -> bf16 -> swizzled smem; row sum in fp32
-        uint8_t* p_row = p_smem + sb * Cfg::kPBytes + r * 128;
+        // P = 2^(x - m_used) -> bf16 -> swizzled smem; row sum in fp32
         const float neg_m = -m_used;
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[16];
 #pragma unroll
-        for (int c = 0; c < KV_TILE; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(s_addr + c, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float e0, e1;
-            if constexpr (!kBias && !kTail) {
-              e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-              e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
-            } else {
-              e0 = ex2_approx(score(v[i], kv0 + c + i) + neg_m);
-              e1 = ex2_approx(score(v[i + 1], kv0 + c + i + 1) + neg_m);
-            }
-            sum[(i >> 1) & 3] += e0 + e1;
-            pk[i >> 1] = pack_bf16(e0, e1);
+        for (int i = 0; i < 32; i += 2) {
+          float e0, e1;
+          if constexpr (!kBias && !kTail) {
+            e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+            e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
+          } else {
+            e0 = ex2_approx(x[i] + neg_m);
+            e1 = ex2_approx(x[i + 1] + neg_m);
           }
-          uint8_t* blk = p_row + (c >> 6) * (128 * 128);
+          sum[(i >> 1) & 3] += e0 + e1;
+#ifdef WFL_EXP_TRUNCPACK  // experiment build only: bf16 by truncation on the ALU pipe instead of F2FP
+          pk[i >> 1] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
+#else
+          pk[i >> 1] = pack_bf16(e0, e1);
+#endif
+        }
+        if constexpr (kPTmem) {
+          // this warp's 32 keys = 16 packed columns of the P tile that overlays S buffer ss (both warps of the pair
+          // finished reading S before pair_sync above, so the overlay is safe)
+#ifndef WFL_EXP_NOSTORE
+          tmem_st16(lane_addr + ss * KV_TILE + ch * 16, pk);
+          tmem_st_wait();
+#else
+          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) tmem_st16(lane_addr + ss * KV_TILE + ch * 16, pk);
+#endif
+        } else {
+          uint8_t* p_row = p_smem + sb * Cfg::kPBytes + r * 128;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const int chunk16 = ((c & 63) >> 3) + q4;
-            *reinterpret_cast<uint4*>(blk + ((chunk16 ^ (r & 7)) << 4)) =
+            const int chunk16 = ch * 4 + q4;
+            *reinterpret_cast<uint4*>(p_row + ((chunk16 ^ (r & 7)) << 4)) =
                 make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
           }
         }
         l_sum += (sum[0] + sum[1]) + (sum[2] + sum[3]);
       };
-      const bool tail = kv0 + KV_TILE > p.T;  // warp-uniform
+      const bool tail = (j + 1) * KV_TILE > p.T;  // CTA-uniform
       if (has_bias) {
         if (tail) tile(std::true_type{}, std::true_type{});
         else tile(std::true_type{}, std::false_type{});
@@ -336,22 +392,31 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (tail) tile(std::false_type{}, std::true_type{});
         else tile(std::false_type{}, std::false_type{});
       }
+#else
+      l_sum = 1.0f;
+      (void)kv0;
+      (void)has_bias;
+#endif
       // S buffer consumed; P visible to the tensor core (async proxy)
       tc_fence_before();
-      fence_proxy_async_smem();
+      if constexpr (!kPTmem) fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&s_empty[sb]);
+        if constexpr (!kPTmem) mbar_arrive(&s_empty[ss]);
         mbar_arrive(&p_full[sb]);
       }
     }
 
     // ---- epilogue: O / l -> bf16 -> (Q's smem, no longer needed) -> TMA store
+    // row sums of the two column halves meet in the exchange buffer the LAST tile did not use
+    float* xsum = xmax + (((n_kv - 1) & 1) ^ 1) * 2 * 128;
+    xsum[ch * 128 + r] = l_sum;
     mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l_sum;
+    pair_sync(quarter);
+    const float inv_l = 1.0f / (l_sum + xsum[(ch ^ 1) * 128 + r]);
 #pragma unroll 1
-    for (int c = 0; c < HD; c += 32) {
+    for (int c = ch * kOHalf; c < (ch + 1) * kOHalf; c += 32) {
       uint32_t o[32];
       tmem_ld32(lane_addr + Cfg::kOCol + c, o);
       tmem_ld_wait();
@@ -368,8 +433,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
     fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
+    pair_sync(quarter);  // both column halves of this quarter's rows are staged
+    if (ch == 0 && lane == 0) {
       for (int jb = 0; jb < Cfg::kHdBlocks; ++jb)
         tma_store_3d(&map_out, q_smem + jb * (128 * 128) + quarter * 32 * 128, h * HD + jb * 64, q0 + quarter * 32, b);
       tma_commit_group();
@@ -385,18 +450,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 }
 
-template <int HD, int KV_TILE, int KV_STAGES>
+template <int HD, int KV_STAGES>
 static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int B, int T, int H,
                             const AttnParams& p, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                             cudaStream_t stream) {
-  using Cfg = AttnCfg<HD, KV_TILE, KV_STAGES>;
+  using Cfg = AttnCfg<HD, KV_STAGES>;
   CUtensorMap mq, mkv, mo;
-  const int64_t width = row_stride;  // any column of the row may be addressed
   {
-    uint64_t dims[3] = {(uint64_t)width, (uint64_t)T, (uint64_t)B};
+    uint64_t dims[3] = {(uint64_t)row_stride, (uint64_t)T, (uint64_t)B};  // any column of the row may be addressed
     uint64_t strides[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
     uint32_t box_q[3] = {64, 128, 1};
-    uint32_t box_kv[3] = {64, (uint32_t)KV_TILE, 1};
+    uint32_t box_kv[3] = {64, (uint32_t)kKvTile, 1};
     int rc = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_q,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -412,7 +476,7 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = attention_kernel<HD, KV_TILE, KV_STAGES>;
+  auto kern = attention_kernel<HD, KV_STAGES>;
   static bool configured = false;
   if (!configured) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -450,14 +514,14 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
   p.gate = gate;
   switch (hd) {
     case 64:
-      return launch_attention<64, 64, 3>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
-                                          out_batch_stride, stream);
+      return launch_attention<64, 3>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride,
+                                     stream);
     case 256:
-      return launch_attention<256, 64, 2>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
-                                          out_batch_stride, stream);
+      return launch_attention<256, 2>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride,
+                                      stream);
     case 384:
-      return launch_attention<384, 64, 1>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
-                                          out_batch_stride, stream);
+      return launch_attention<384, 1>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride,
+                                      stream);
     default:
       if (rel_bias != nullptr) {
         set_error("wfl_attention: relative-position bias is only built for head_dim 64/256/384 (got %d)", hd);

@@ -147,8 +147,8 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer
+  } else if (warp == 1 || warp == 2) {
+    // ===== MMA issuers: warp 1 issues the score MMAs, warp 2 the PV MMAs (one issuing thread paces the kernel)
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kBigKv, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, Cfg::kPvN1, 0, 1);
@@ -206,10 +206,10 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         umma_commit(&pv_done[sb]);
       };
 
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        issue_pv(j);
+      if (warp == 1) {
+        for (int j = 0; j < n_kv; ++j) issue_qk(j);
+      } else {
+        for (int j = 0; j < n_kv; ++j) issue_pv(j);
       }
     }
   } else if (warp >= 4) {
