@@ -190,7 +190,11 @@ def run_ours(args, rank, world, local_rank):
         achieved = fl / (tms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": f"gemm_kernel[{tag}]", "achieved": round(achieved, 1),
                     "peak": peaks["tf_sustained"], "peak_source": peaks["src"] + " (sustained bf16 dense)",
-                    "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
+                    "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sustained"], 4),
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this kernel on
+                    # this shape (profiles/r01_conv31_gemm_full.ncu-rep); algorithmic bytes are 114.7 MB, part of the
+                    # 49 MB output is still dirty in L2 when the kernel ends
+                    "traffic": 85.1e6 if WORKLOAD == "cfg2" else None, "traffic_unit": "bytes/launch",
                     "launches": n, "avg_launch_ms": round(tms / n, 4),
                     "algorithmic_flop_per_launch": fl / n,
                     "gemm_family": {"note": "all wfl_gemm launches, measured in a separate event-instrumented pass",
@@ -201,14 +205,21 @@ def run_ours(args, rank, world, local_rank):
     value = audio_s_per_step * world * args.steps / (ms * 1e-3)
     e2e_value = audio_s_per_step * world * args.steps / (ms_e2e * 1e-3)
     h2d = host_sets[0].numel() * 4
-    d2h = batch * 1500 * 24 + batch * 4 * 2
+    frames = int(labeler._ws and next(iter(labeler._ws))[1] or 1500)
+    d2h = batch * frames * 24 + batch * 4 * 2
+    m = cfg["model"]
+    arch_txt = (f"{m['whisper_model'] if m['encoder_type'] == 'whisper' else m['wavlm_model']} encoder"
+                f"{' + BiLSTM(' + str(m.get('bilstm_num_layer', 1)) + ')' if m.get('enable_bilstm', True) else ''}"
+                f" + {m['num_conformer_layers']} Conformer (heads {m['conformer_heads']}, ffx {m['conformer_ff_expansion']}, "
+                f"k{m['conformer_kernel_size']}){' + dilated conv stack' if m.get('enable_dilated_conv', True) else ''}")
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: whisper-base encoder + 4 Conformer (heads 2, ffx 2, k31) + median 5 + "
-                               f"merge right, batch {batch} x {wl['seconds']:.0f} s per GPU, L=61, lang_id=0, random init",
-                   "batch_per_gpu": batch, "clip_seconds": wl["seconds"], "frames_per_clip": 1500,
+        "config": {"workload": f"BASELINE configs[{int(WORKLOAD[3:]) - 1}] ({WORKLOAD}): {arch_txt} + median {pp['median_filter']} + "
+                               f"merge {pp['merge_segments']}, batch {batch} x {wl['seconds']:.0f} s per GPU, L=61, lang_id=0, "
+                               f"random init",
+                   "batch_per_gpu": batch, "clip_seconds": wl["seconds"], "frames_per_clip": frames,
                    "l2_policy": "inputs alternate between two batches; per-step working set (~1.5 GB of activations) exceeds the 126 MB L2",
                    "parallelism": f"utterance-sharded x{world}, no hot-path collective"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
