@@ -39,11 +39,12 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP based, ~1e-6 absolute error (the recurrent operand h is rounded to bf16 anyway)
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) {
-  // tanh(x) = 1 - 2 / (1 + e^{2x}); saturates cleanly for large |x|
+  // tanh(x) = 1 - 2 / (1 + e^{2x}); saturates cleanly for large |x| (e = inf -> 1, e = 0 -> -1)
   const float e = __expf(2.0f * x);
-  return 1.0f - 2.0f / (1.0f + e);
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
 
 // CL = CTAs per cluster: 8 (portable) up to H = 384; 16 (non-portable, opt-in) for H = 512 / 640 so that each CTA's
@@ -130,14 +131,26 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
     const int t = dir == 0 ? s : T - 1 - s;
     const int cur = s & 1, nxt = cur ^ 1;
     // ---- W_hh h_{t-1} for this warp's 16 gate rows x 2 tiles x 8 batch columns over its K half
+    // four independent accumulator chains (even / odd k-tiles) halve the dependent-MMA latency chain
     float acc_if[4] = {0.f, 0.f, 0.f, 0.f}, acc_go[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc_if2[4] = {0.f, 0.f, 0.f, 0.f}, acc_go2[4] = {0.f, 0.f, 0.f, 0.f};
     const __nv_bfloat16* hrow = hbuf + (cur * kLstmNB + g) * Cfg::kHStride + khalf * Cfg::kKTiles * 16 + 2 * q;
 #pragma unroll
     for (int kt = 0; kt < Cfg::kKTiles; ++kt) {
       const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16);
       const uint32_t hb1 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16 + 8);
-      mma_bf16_16816(acc_if, wa[kt], hb0, hb1);
-      mma_bf16_16816(acc_go, wb[kt], hb0, hb1);
+      if (kt & 1) {
+        mma_bf16_16816(acc_if2, wa[kt], hb0, hb1);
+        mma_bf16_16816(acc_go2, wb[kt], hb0, hb1);
+      } else {
+        mma_bf16_16816(acc_if, wa[kt], hb0, hb1);
+        mma_bf16_16816(acc_go, wb[kt], hb0, hb1);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc_if[i] += acc_if2[i];
+      acc_go[i] += acc_go2[i];
     }
     if (khalf == 1) {
       float4* pp = reinterpret_cast<float4*>(part + (group * 32 + lane) * 8);
@@ -148,18 +161,20 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
     if (khalf == 0) {
       const float4* pp = reinterpret_cast<const float4*>(part + (group * 32 + lane) * 8);
       const float4 p_if = pp[0], p_go = pp[1];
-      // prefetch the next step's input pre-activations while this step's math runs
-      float4 nx0 = pre0, nx1 = pre1;
+      // this step's input pre-activations were requested one step ago; take them, then immediately request the next
+      // step's.  (Nothing may read pre0/pre1 again before the next iteration: a register copy of the in-flight load at
+      // the end of this block stalled ~1100 cycles per step on the scoreboard -- per-phase clock64 trace, profiles/.)
+      const float4 in0 = pre0, in1 = pre1;
       if (s + 1 < T) {
         const int tn = dir == 0 ? s + 1 : T - 2 - s;
-        if (bq0 < B) nx0 = __ldg(gx_ptr(bq0, tn));
-        if (bq1 < B) nx1 = __ldg(gx_ptr(bq1, tn));
+        if (bq0 < B) pre0 = __ldg(gx_ptr(bq0, tn));
+        if (bq1 < B) pre1 = __ldg(gx_ptr(bq1, tn));
       }
       // accumulator layout: [0],[1] = first gate of the tile (rows g) for batch 2q, 2q+1; [2],[3] = second gate (rows g+8)
-      const float ai0 = acc_if[0] + p_if.x + pre0.x, ai1 = acc_if[1] + p_if.y + pre1.x;
-      const float af0 = acc_if[2] + p_if.z + pre0.y, af1 = acc_if[3] + p_if.w + pre1.y;
-      const float ag0 = acc_go[0] + p_go.x + pre0.z, ag1 = acc_go[1] + p_go.y + pre1.z;
-      const float ao0 = acc_go[2] + p_go.z + pre0.w, ao1 = acc_go[3] + p_go.w + pre1.w;
+      const float ai0 = acc_if[0] + p_if.x + in0.x, ai1 = acc_if[1] + p_if.y + in1.x;
+      const float af0 = acc_if[2] + p_if.z + in0.y, af1 = acc_if[3] + p_if.w + in1.y;
+      const float ag0 = acc_go[0] + p_go.x + in0.z, ag1 = acc_go[1] + p_go.y + in1.z;
+      const float ao0 = acc_go[2] + p_go.z + in0.w, ao1 = acc_go[3] + p_go.w + in1.w;
       c_state[0] = sigmoid_acc(af0) * c_state[0] + sigmoid_acc(ai0) * tanh_acc(ag0);
       c_state[1] = sigmoid_acc(af1) * c_state[1] + sigmoid_acc(ai1) * tanh_acc(ag1);
       const float h0 = sigmoid_acc(ao0) * tanh_acc(c_state[0]);
@@ -171,8 +186,6 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
         if (bq0 < B) y_f32[(static_cast<int64_t>(bq0) * T + t) * (2 * H) + dir * H + unit] = h0;
         if (bq1 < B) y_f32[(static_cast<int64_t>(bq1) * T + t) * (2 * H) + dir * H + unit] = h1;
       }
-      pre0 = nx0;
-      pre1 = nx1;
     }
     __syncthreads();
     // ---- push this CTA's slice of h_t to every CTA of the cluster (and to global as bf16)
