@@ -215,7 +215,10 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "fp16",
+        "dtype_note": "IEEE fp16 operands (same tcgen05 kind::f16 rate and width as bf16, 11-bit significand), fp32 accumulate, "
+                      "fp32 residual stream / normalisation / softmax / LSTM cell",
+        "data": "synthetic",
         "config": {"workload": f"BASELINE configs[{int(WORKLOAD[3:]) - 1}] ({WORKLOAD}): {arch_txt} + median {pp['median_filter']} + "
                                f"merge {pp['merge_segments']}, batch {batch} x {wl['seconds']:.0f} s per GPU, L=61, lang_id=0, "
                                f"random init",

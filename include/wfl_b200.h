@@ -49,20 +49,20 @@ int wfl_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 enum wfl_act { WFL_ACT_NONE = 0, WFL_ACT_GELU = 1, WFL_ACT_RELU = 2 };
 enum wfl_out_mode {
-  WFL_OUT_STORE_BF16 = 0, /* out_bf16 = act(acc + bias)                                  */
+  WFL_OUT_STORE_F16 = 0, /* out_f16 = act(acc + bias)                                  */
   WFL_OUT_STORE_F32 = 1,  /* out_f32  = act(acc + bias)                                  */
   WFL_OUT_ADD_F32 = 2,    /* out_f32 += alpha * act(acc + bias)   (residual stream)      */
-  WFL_OUT_GLU_BF16 = 3    /* out_bf16[:, j] = (acc_a + b_a) * sigmoid(acc_g + b_g); weights are packed so that
+  WFL_OUT_GLU_F16 = 3    /* out_f16[:, j] = (acc_a + b_a) * sigmoid(acc_g + b_g); weights are packed so that
                              every block of `glu_block` output rows holds glu_block/2 value rows followed by the
                              matching glu_block/2 gate rows (REF/model.py:31-32)          */
 };
 
 typedef struct wfl_gemm_desc {
-  /* A: bf16, logical [batches][a_rows][a_cols], a_cols contiguous */
+  /* A: f16, logical [batches][a_rows][a_cols], a_cols contiguous */
   const void* a;
   int64_t a_rows, a_cols, a_row_stride, a_batch_stride; /* strides in elements */
   int32_t batches;
-  /* W: bf16 [n][num_slabs * slab_k], K contiguous */
+  /* W: f16 [n][num_slabs * slab_k], K contiguous */
   const void* w;
   int32_t n, slab_k, num_slabs;
   int32_t slab_row_shift[WFL_MAX_SLABS];
@@ -72,7 +72,7 @@ typedef struct wfl_gemm_desc {
   int64_t bias_batch_stride; /* elements */
   int32_t act, out_mode;
   float alpha;
-  void* out; /* bf16 or f32, logical [batches][m_rows][out_cols] */
+  void* out; /* f16 or f32, logical [batches][m_rows][out_cols] */
   int64_t m_rows, out_row_stride, out_batch_stride; /* elements */
   int32_t tile_n;                                     /* 0 = auto, else 64/128/256 */
 } wfl_gemm_desc;
@@ -81,7 +81,7 @@ int wfl_gemm(const wfl_gemm_desc* desc, void* stream);
 
 /* ---- K9: fused flash attention (tcgen05, online softmax) -------------------------------------
  * out[b, t, h*hd:(h+1)*hd] = softmax_k(scale * q.k + gate[b,h,t] * rel_bias[h, k - t + T - 1]) v
- * q/k/v are column slices of one bf16 buffer [B][T][row_stride] (q_col/k_col/v_col = column of
+ * q/k/v are column slices of one f16 buffer [B][T][row_stride] (q_col/k_col/v_col = column of
  * head 0).  rel_bias/gate may be NULL (Whisper TF/.../modeling_whisper.py:284-357; Conformer
  * nn.MultiheadAttention REF/model.py:26,42); both set = WavLM gated relative position bias
  * (TF/models/wavlm/modeling_wavlm.py:147-241).
@@ -91,53 +91,53 @@ int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int
                   const float* gate, void* out, int64_t out_row_stride, int64_t out_batch_stride, void* stream);
 
 /* ---- K8: LayerNorm (fp32 statistics) ----------------------------------------------------------
- * y = LN(x; gamma, beta); out_f32 (nullable) receives y; out_bf16 (nullable) receives y, or
+ * y = LN(x; gamma, beta); out_f32 (nullable) receives y; out_f16 (nullable) receives y, or
  * LN(y; gamma2, beta2) when gamma2 != NULL (REF/model.py:43-44: x = ln1(x + attn); ln2(x)).
- * out_f32 may alias x.  nn.LayerNorm eps = 1e-5 everywhere on the path.  act_bf16 = WFL_ACT_GELU applies
- * GELU to the bf16 output only (WavLM-large conv layers: conv -> LayerNorm -> GELU,
+ * out_f32 may alias x.  nn.LayerNorm eps = 1e-5 everywhere on the path.  act_f16 = WFL_ACT_GELU applies
+ * GELU to the f16 output only (WavLM-large conv layers: conv -> LayerNorm -> GELU,
  * TF/models/wavlm/modeling_wavlm.py:703-727).
  */
 int wfl_layernorm(const float* x, int64_t rows, int32_t d, const float* gamma, const float* beta,
-                  const float* gamma2, const float* beta2, float eps, float* out_f32, void* out_bf16,
-                  int32_t act_bf16, void* stream);
+                  const float* gamma2, const float* beta2, float eps, float* out_f32, void* out_f16,
+                  int32_t act_f16, void* stream);
 
 /* ---- K3: WavLM conv layer 0 (TF/models/wavlm/modeling_wavlm.py:730-751 group / :703-727 layer) ----------
  * Conv1d(1, 512, k=10, s=5, no bias) + {norm_mode 0: GroupNorm(512 groups) = per-channel statistics over all
  * T0 = (n_samples-10)/5+1 frames of each clip; norm_mode 1: zero-mean/unit-variance waveform
  * (TF/models/wav2vec2/feature_extraction_wav2vec2.py:77-97) then LayerNorm over channels} + GELU.
- * wave fp32 [B][wave_stride]; w fp32 [512][10]; out bf16 [B][out_batch_stride] rows of 512 channels.
+ * wave fp32 [B][wave_stride]; w fp32 [512][10]; out f16 [B][out_batch_stride] rows of 512 channels.
  * scratch_stats: (2 + 1024) * B doubles.  The pre-norm activations are recomputed, never stored.
  */
 int wfl_wavlm_conv0(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, const float* w,
-                    const float* gamma, const float* beta, int32_t norm_mode, void* out_bf16,
+                    const float* gamma, const float* beta, int32_t norm_mode, void* out_f16,
                     int64_t out_batch_stride, double* scratch_stats, void* stream);
 
 /* ---- K10: WavLM gated relative position bias gate (TF/models/wavlm/modeling_wavlm.py:159-176) -------------
  * gate[b][h][t] = ga * (gb * gate_const[h] - 1) + 2, (ga, gb) = sigmoid(sum over 4 of Linear(hd -> 8)(x[b,t,head h])).
- * x bf16 [B*T][row_stride]; gate_w fp32 [8][hd]; gate fp32 [B][H][T] (input of wfl_attention).
+ * x f16 [B*T][row_stride]; gate_w fp32 [8][hd]; gate fp32 [B][H][T] (input of wfl_attention).
  */
-int wfl_wavlm_gate(const void* x_bf16, int64_t row_stride, int32_t B, int32_t T, int32_t H, int32_t hd,
+int wfl_wavlm_gate(const void* x_f16, int64_t row_stride, int32_t B, int32_t T, int32_t H, int32_t hd,
                    const float* gate_w, const float* gate_b, const float* gate_const, float* gate, void* stream);
 
-/* fp32 [rows][d] -> bf16 [rows][2d] = [hi | lo] with hi = bf16(x), lo = bf16(x - hi): operands for the
+/* fp32 [rows][d] -> f16 [rows][2d] = [hi | lo] with hi = f16(x), lo = f16(x - hi): operands for the
  * split-precision (3-slab) tail GEMMs (classifier REF/model.py:135,192). */
-int wfl_split_bf16(const float* x, int64_t rows, int32_t d, void* out_hi_lo, void* stream);
+int wfl_split_f16(const float* x, int64_t rows, int32_t d, void* out_hi_lo, void* stream);
 
 /* dst[b][t][:] = src[t][:] for b < batches (positional embedding broadcast before the conv2
  * epilogue accumulates into it; TF/models/whisper/modeling_whisper.py:622-625). */
 int wfl_broadcast_rows(const float* src, int64_t rows, int32_t d, int32_t batches, float* dst, void* stream);
 
 /* out[r][j] = sigmoid(dot(x[r], w[j]) + b[j]), j < n_out <= 4: the 1x1 conv + Sigmoid that ends the
- * boundary-offset head (REF/model.py:140-141,193).  x bf16 [rows][d], w fp32 [n_out][d]. */
-int wfl_rowdot_sigmoid(const void* x_bf16, int64_t rows, int32_t d, const float* w, const float* b, int32_t n_out,
+ * boundary-offset head (REF/model.py:140-141,193).  x f16 [rows][d], w fp32 [n_out][d]. */
+int wfl_rowdot_sigmoid(const void* x_f16, int64_t rows, int32_t d, const float* w, const float* b, int32_t n_out,
                        float* out, void* stream);
 
 /* ---- K11: bidirectional LSTM recurrence (persistent cluster kernel; nn.LSTM at REF/model.py:105-111,183) ----
  * One layer, both directions.  gx fp32 [B][T][8H] = x W_ih^T + b_ih + b_hh computed by wfl_gemm with the
- * output columns packed [dir][unit][gate i,f,g,o]; whh bf16 [2][4H][H] (nn.LSTM row order, gate-major).
- * Writes h_t as [B][T][2H] = [fwd | bwd] to y_bf16 and/or y_f32 (either may be NULL).  h0 = c0 = 0.
+ * output columns packed [dir][unit][gate i,f,g,o]; whh f16 [2][4H][H] (nn.LSTM row order, gate-major).
+ * Writes h_t as [B][T][2H] = [fwd | bwd] to y_f16 and/or y_f32 (either may be NULL).  h0 = c0 = 0.
  */
-int wfl_lstm_layer(const float* gx, const void* whh_bf16, int32_t B, int32_t T, int32_t H, void* y_bf16,
+int wfl_lstm_layer(const float* gx, const void* whh_f16, int32_t B, int32_t T, int32_t H, void* y_f16,
                    float* y_f32, void* stream);
 
 /* ---- K0: peak normalisation (REF/infer.py:234-235 and per chunk :114-115) ---------------------
@@ -154,14 +154,14 @@ int wfl_peak_normalize(const double* in, const int64_t* clip_begin, int32_t n_cl
 /* ---- K1: Whisper log-mel front-end (TF/models/whisper/feature_extraction_whisper.py:135-164) --
  * wave fp32 [B][wave_stride] (n_samples valid, zero-extended/truncated to 480000).  The windowed DFT is a
  * tensor-core contraction over an overlapping-row view of the reflect-padded waveform in split precision
- * (hi*hi + hi*mid + mid*hi): basis_split_bf16 is bf16 [448][3*448] = [W_hi | W_mid | W_hi] with
+ * (hi*hi + hi*mid + mid*hi): basis_split_f16 is f16 [448][3*448] = [W_hi | W_mid | W_hi] with
  * W[n][k] = hann[k] * {cos, -sin}(2 pi (n/2) k / 400) for output column n (cos/-sin interleaved per bin), zero padded.
  * Then power, mel (filters fp32 [201][n_mels]), log10(clamp 1e-10), per-clip max-8 floor, (x+4)/4.
- * out bf16 [B][3000][out_stride] (channels >= n_mels zeroed).  scratch_planes: bf16 2*480480*B + 4096 elements;
+ * out f16 [B][3000][out_stride] (channels >= n_mels zeroed).  scratch_planes: f16 2*480480*B + 4096 elements;
  * scratch_dft: fp32 [B][3000][448]; scratch_logspec: fp32 [B][3000][n_mels]; scratch_max: B floats.
  */
 int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B,
-                       const void* basis_split_bf16, const float* mel_filters, int32_t n_mels, void* out_bf16,
+                       const void* basis_split_f16, const float* mel_filters, int32_t n_mels, void* out_f16,
                        int32_t out_stride, void* scratch_planes, float* scratch_dft, float* scratch_logspec,
                        float* scratch_max, void* stream);
 

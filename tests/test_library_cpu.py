@@ -31,9 +31,9 @@ def test_library_exports_header_symbols():
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_compute_fails_loudly_without_gpu():
     from wfl_asr_b200 import ops
-    a = torch.zeros(128, 64, dtype=torch.bfloat16)
+    a = torch.zeros(128, 64, dtype=torch.float16)
     with pytest.raises(ops.WflError):
-        ops.linear(a, a, torch.zeros(128, 128, dtype=torch.bfloat16))
+        ops.linear(a, a, torch.zeros(128, 128, dtype=torch.float16))
     from wfl_asr_b200 import utils
     with pytest.raises(ops.WflError):
         utils.decode_bio_tags(["O", "B-a"])
@@ -79,7 +79,7 @@ def test_packing_folds():
     wg, bg = packing.interleave_glu(torch.arange(16.0)[:, None].repeat(1, 3), torch.arange(16.0), 8)
     assert bg.tolist() == [0, 1, 2, 3, 8, 9, 10, 11, 4, 5, 6, 7, 12, 13, 14, 15]
     w3 = packing.split_hi_lo(torch.randn(4, 8, generator=g))
-    assert w3.shape == (4, 24) and w3.dtype == torch.bfloat16
+    assert w3.shape == (4, 24) and w3.dtype == torch.float16
 
 
 def test_label_tables_and_alignment():

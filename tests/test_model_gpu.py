@@ -61,10 +61,13 @@ def test_forward_matches_oracle(name):
     # the oracle itself is pinned to the reference by tests/test_oracle_forward.py; cross-check the fixture too
     assert (ref_l[:, ::mfg.STRIDE] - torch.from_numpy(GOLD[name + "/logits"])).abs().max().item() <= 2e-5 * max(1.0, ref_l.abs().max().item())
     rel, agree, agree_safe, off_err = _compare(name, logits, offsets, ref_l, ref_o)
-    assert rel <= 1e-2, f"logit error {rel} above the bf16 tolerance 1e-2"
+    # north_star tolerance: 1e-2 of the logit scale.  fp16 operands + fp32 accumulation measure 3e-4 .. 1e-3, so the
+    # test holds the implementation to 2e-3; tag agreement target 99.9 % (measured 99.90 .. 100 %; the bar below
+    # leaves room for one or two near-tie frames at these small test sizes)
+    assert rel <= 2e-3, f"logit error {rel} above the fp16 bar 2e-3 (north_star tolerance 1e-2)"
     assert agree_safe == 1.0
-    assert agree >= 0.97
-    assert off_err <= 2e-2
+    assert agree >= 0.998
+    assert off_err <= 2e-3
 
 
 def test_lang_none_skips_projection():
@@ -73,7 +76,7 @@ def test_lang_none_skips_projection():
     logits, offsets = model(wave.to(DEV), None)
     ref_l, ref_o = to.forward(wave, sd, cfg, None)
     rel, agree, agree_safe, _ = _compare(name + "/lang=None", logits.float().cpu(), offsets.float().cpu(), ref_l, ref_o)
-    assert rel <= 1e-2 and agree_safe == 1.0
+    assert rel <= 2e-3 and agree_safe == 1.0
 
 
 def test_cpu_input_fails_loudly():
@@ -191,7 +194,7 @@ def test_infer_audio_end_to_end(tmp_path, seconds):
     expect = po.merge_adjacent_segments(all_segs, "right")
     print(f"[infer {seconds}s] {len(segs)} segments; frame-tag agreement with the fp32 oracle {n_agree / n_frames:.4%}")
     assert segs == expect
-    assert n_agree / n_frames >= 0.97
+    assert n_agree / n_frames >= 0.995
 
 
 def test_full_size_cfg2_properties():
@@ -217,7 +220,7 @@ def test_full_size_cfg2_properties():
         assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch 32 and batch 1"
     ref_l, ref_o = to.forward(wave[13:14], sd, cfg, lang[13:14].cpu())
     rel, agree, agree_safe, off_err = _compare("cfg2 full size, clip 13", l1[13:14].float().cpu(), o1[13:14].float().cpu(), ref_l, ref_o)
-    assert rel <= 1e-2 and agree_safe == 1.0
+    assert rel <= 2e-3 and agree_safe == 1.0
     lab = Labeler(model, median_filter=5, merge_mode="right", confidence_threshold=0.5)
     ids, merged, nout, fcb, n_files = lab.postprocess(l1, o1)
     segs = lab.fetch(merged, nout, fcb, n_files, 1500)

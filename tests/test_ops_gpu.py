@@ -38,11 +38,11 @@ def _report(name, got, ref, tol):
 # ----------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("tile_n", [128, 256])
 @pytest.mark.parametrize("M,K,N", [(128, 64, 256), (300, 128, 256), (1000, 512, 512), (257, 192, 384)])
-def test_gemm_linear_bf16(M, K, N, tile_n):
-    a = _rand(M, K, seed=1).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=2).bfloat16()
+def test_gemm_linear_f16(M, K, N, tile_n):
+    a = _rand(M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
     bias = _rand(N, seed=3)
-    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
     ops.linear(a, w, out, bias=bias, tile_n=tile_n)
     ref = a.float() @ w.float().T + bias
     _report("linear", out, ref, 1e-2)
@@ -51,10 +51,10 @@ def test_gemm_linear_bf16(M, K, N, tile_n):
 @pytest.mark.parametrize("act", [ops.ACT_GELU, ops.ACT_RELU])
 def test_gemm_activations(act):
     M, K, N = 384, 256, 512
-    a = _rand(M, K, seed=4).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=5).bfloat16()
+    a = _rand(M, K, seed=4).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=5).half()
     bias = _rand(N, seed=6)
-    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float16)
     ops.linear(a, w, out, bias=bias, act=act)
     pre = a.float() @ w.float().T + bias
     ref = F.gelu(pre) if act == ops.ACT_GELU else F.relu(pre)
@@ -64,8 +64,8 @@ def test_gemm_activations(act):
 @pytest.mark.parametrize("tile_n", [128, 256])
 def test_gemm_f32_store_and_add(tile_n):
     M, K, N = 500, 128, 256
-    a = _rand(M, K, seed=7).bfloat16()
-    w = _rand(N, K, scale=K ** -0.5, seed=8).bfloat16()
+    a = _rand(M, K, seed=7).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=8).half()
     bias = _rand(N, seed=9)
     ref = a.float() @ w.float().T + bias
     out = torch.empty(M, N, device=DEV)
@@ -79,13 +79,13 @@ def test_gemm_f32_store_and_add(tile_n):
 
 def test_gemm_glu():
     M, K, d = 300, 128, 256
-    a = _rand(M, K, seed=11).bfloat16()
-    w = _rand(2 * d, K, scale=K ** -0.5, seed=12).bfloat16()
+    a = _rand(M, K, seed=11).half()
+    w = _rand(2 * d, K, scale=K ** -0.5, seed=12).half()
     bias = _rand(2 * d, seed=13)
     from wfl_asr_b200.packing import interleave_glu
     wp, bp = interleave_glu(w, bias, 256)
-    out = torch.empty(M, d, device=DEV, dtype=torch.bfloat16)
-    ops.linear(a, wp, out, bias=bp, out_mode=ops.OUT_GLU_BF16, tile_n=256)
+    out = torch.empty(M, d, device=DEV, dtype=torch.float16)
+    ops.linear(a, wp, out, bias=bp, out_mode=ops.OUT_GLU_F16, tile_n=256)
     pre = a.float() @ w.float().T + bias
     ref = pre[:, :d] * torch.sigmoid(pre[:, d:])
     _report("glu", out, ref, 1e-2)
@@ -95,12 +95,12 @@ def test_gemm_glu():
 def test_gemm_conv1d(ksize, dil):
     """Conv1d(C, N, k, dilation, padding=dil*(k-1)//2) over [B, T, C] as shifted K-slabs."""
     B, T, C, N = 3, 200, 128, 256
-    x = _rand(B, T, C, seed=14).bfloat16()
-    wt = _rand(N, C, ksize, scale=(C * ksize) ** -0.5, seed=15).bfloat16()
+    x = _rand(B, T, C, seed=14).half()
+    wt = _rand(N, C, ksize, scale=(C * ksize) ** -0.5, seed=15).half()
     bias = _rand(N, seed=16)
     pad = dil * (ksize - 1) // 2
     w2 = wt.permute(0, 2, 1).contiguous().view(N, ksize * C)  # [N][tap][C]
-    out = torch.empty(B, T, N, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(B, T, N, device=DEV, dtype=torch.float16)
     ops.gemm(x, w2, out, n=N, slab_k=C, shifts=[j * dil - pad for j in range(ksize)], cols=[0] * ksize, a_rows=T,
              a_cols=C, a_row_stride=C, a_batch_stride=T * C, batches=B, m_rows=T, out_row_stride=N,
              out_batch_stride=T * N, bias=bias)
@@ -111,12 +111,12 @@ def test_gemm_conv1d(ksize, dil):
 def test_gemm_conv_stride2():
     """Whisper conv2 (k3, s2, p1) through the paired-row view [T/2, 2C]."""
     B, T, C, N = 2, 300, 128, 256
-    x = _rand(B, T, C, seed=17).bfloat16()
-    wt = _rand(N, C, 3, scale=(3 * C) ** -0.5, seed=18).bfloat16()
+    x = _rand(B, T, C, seed=17).half()
+    wt = _rand(N, C, 3, scale=(3 * C) ** -0.5, seed=18).half()
     bias = _rand(N, seed=19)
     w2 = wt.permute(0, 2, 1).contiguous().view(N, 3 * C)
     To = T // 2
-    out = torch.empty(B, To, N, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(B, To, N, device=DEV, dtype=torch.float16)
     ops.gemm(x, w2, out, n=N, slab_k=C, shifts=[-1, 0, 0], cols=[C, 0, C], a_rows=To, a_cols=2 * C,
              a_row_stride=2 * C, a_batch_stride=T * C, batches=B, m_rows=To, out_row_stride=N,
              out_batch_stride=To * N, bias=bias, act=ops.ACT_GELU)
@@ -129,11 +129,11 @@ def test_gemm_batched_bias_and_split_precision():
     x = _rand(B, T, d, seed=20)
     w = _rand(N, d, scale=d ** -0.5, seed=21)
     bias = _rand(B, N, seed=22)
-    hl = torch.empty(B, T, 2 * d, device=DEV, dtype=torch.bfloat16)
-    ops.split_bf16(x, hl)
-    assert torch.equal(hl[..., :d], x.bfloat16())
-    w_hi = w.bfloat16()
-    w_lo = (w - w_hi.float()).bfloat16()
+    hl = torch.empty(B, T, 2 * d, device=DEV, dtype=torch.float16)
+    ops.split_f16(x, hl)
+    assert torch.equal(hl[..., :d], x.half())
+    w_hi = w.half()
+    w_lo = (w - w_hi.float()).half()
     w3 = torch.cat([w_hi, w_hi, w_lo], dim=1).contiguous()
     out = torch.empty(B, T, N, device=DEV)
     ops.gemm(hl, w3, out, n=N, slab_k=d, shifts=[0, 0, 0], cols=[0, d, 0], a_rows=T, a_cols=2 * d, a_row_stride=2 * d,
@@ -144,9 +144,9 @@ def test_gemm_batched_bias_and_split_precision():
 
 
 def test_gemm_rejects_bad_arguments():
-    a = torch.zeros(128, 100, device=DEV, dtype=torch.bfloat16)
-    w = torch.zeros(64, 100, device=DEV, dtype=torch.bfloat16)
-    out = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
+    a = torch.zeros(128, 100, device=DEV, dtype=torch.float16)
+    w = torch.zeros(64, 100, device=DEV, dtype=torch.float16)
+    out = torch.zeros(128, 64, device=DEV, dtype=torch.float16)
     with pytest.raises(ops.WflError):
         ops.linear(a, w, out)  # K not a multiple of 64
 
@@ -169,8 +169,8 @@ def _attn_ref(qkv, B, T, H, hd, scale, bias=None):
                                        (512, 2, 1499, 1)])
 def test_attention(hd, H, T, B):
     d = H * hd
-    qkv = _rand(B, T, 3 * d, seed=23).bfloat16()
-    out = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    qkv = _rand(B, T, 3 * d, seed=23).half()
+    out = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.float16)
     scale = hd ** -0.5
     ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=scale, q_col=0, k_col=d, v_col=2 * d)
     ref = _attn_ref(qkv, B, T, H, hd, scale)
@@ -185,8 +185,8 @@ def test_attention_peaky_scores_rescale():
     qkv[..., :2 * d] *= 3.0
     ramp = torch.linspace(0.2, 3.0, T, device=DEV)[None, :, None]
     qkv[..., d:2 * d] *= ramp  # later keys score higher -> max keeps growing
-    qkv = qkv.bfloat16()
-    out = torch.empty(B, T, d, device=DEV, dtype=torch.bfloat16)
+    qkv = qkv.half()
+    out = torch.empty(B, T, d, device=DEV, dtype=torch.float16)
     ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=1.0, q_col=0, k_col=d, v_col=2 * d)
     _report("attention rescale", out, _attn_ref(qkv, B, T, H, hd, 1.0), 2e-2)
 
@@ -194,7 +194,7 @@ def test_attention_peaky_scores_rescale():
 def test_attention_wavlm_bias():
     hd, H, T, B = 64, 4, 260, 2
     d = H * hd
-    qkv = _rand(B, T, 3 * d, seed=25).bfloat16()
+    qkv = _rand(B, T, 3 * d, seed=25).half()
     emb = _rand(320, H, seed=26)
     gate = (torch.rand(B, H, T, generator=torch.Generator().manual_seed(27)) * 2).to(DEV)
     buckets = to.wavlm_rel_buckets(T).to(DEV)
@@ -207,7 +207,7 @@ def test_attention_wavlm_bias():
     for r in range(-(T - 1), T):
         q_, k_ = (0, r) if r >= 0 else (-r, 0)
         table[:, r + T - 1] = pos_bias[:, q_, k_]
-    out = torch.empty(B, T, d, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(B, T, d, device=DEV, dtype=torch.float16)
     scale = hd ** -0.5
     ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=scale, q_col=0, k_col=d, v_col=2 * d,
                   rel_bias=table.contiguous(), gate=gate.contiguous())
@@ -224,12 +224,12 @@ def test_layernorm(d):
     ref1 = F.layer_norm(x, (d,), g1, b1, 1e-5)
     ref2 = F.layer_norm(ref1, (d,), g2, b2, 1e-5)
     o32 = torch.empty_like(x)
-    o16 = torch.empty(rows, d, device=DEV, dtype=torch.bfloat16)
-    ops.layernorm(x, g1, b1, out_f32=o32, out_bf16=o16)
+    o16 = torch.empty(rows, d, device=DEV, dtype=torch.float16)
+    ops.layernorm(x, g1, b1, out_f32=o32, out_f16=o16)
     _report("ln f32", o32, ref1, 2e-6)
-    _report("ln bf16", o16, ref1, 8e-3)
-    ops.layernorm(x, g1, b1, out_f32=o32, out_bf16=o16, gamma2=g2, beta2=b2)
-    _report("ln2 bf16", o16, ref2, 8e-3)
+    _report("ln f16", o16, ref1, 8e-3)
+    ops.layernorm(x, g1, b1, out_f32=o32, out_f16=o16, gamma2=g2, beta2=b2)
+    _report("ln2 f16", o16, ref2, 8e-3)
     xin = x.clone()
     ops.layernorm(xin, g1, b1, out_f32=xin)  # in place
     _report("ln inplace", xin, ref1, 2e-6)
@@ -240,7 +240,7 @@ def test_broadcast_and_rowdot():
     dst = torch.empty(3, 150, 64, device=DEV)
     ops.broadcast_rows(src, dst, 3)
     assert torch.equal(dst, src[None].expand(3, -1, -1))
-    x = _rand(777, 512, seed=34).bfloat16()
+    x = _rand(777, 512, seed=34).half()
     w, b = _rand(2, 512, scale=0.05, seed=35), _rand(2, seed=36)
     out = torch.empty(777, 2, device=DEV)
     ops.rowdot_sigmoid(x, w, b, out)
@@ -272,16 +272,16 @@ def test_whisper_logmel(n_mels):
     for i, w in enumerate(waves):
         wave[i, :len(w)] = w
     basis, filt = whisper_frontend_constants(n_mels, DEV)
-    out = torch.empty(B, 3000, 128, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(B, 3000, 128, device=DEV, dtype=torch.float16)
     scratch = ops.logmel_scratch(B, n_mels, DEV)
     s1 = scratch[2]
     ops.whisper_logmel(wave.to(DEV), 480000, basis, filt, n_mels, out, scratch)
     ref = to.whisper_log_mel(wave, n_mels).transpose(1, 2)  # [B, 3000, n_mels]
     got = out[..., :n_mels].float().cpu()
     assert not out[..., n_mels:].any()
-    # fp32 log-mel before the bf16 rounding of the output: check the scratch against the oracle pre-normalisation
+    # fp32 log-mel before the f16 rounding of the output: check the scratch against the oracle pre-normalisation
     err = (got - ref).abs().max().item()
-    assert err <= 1.2e-2, err  # bf16 rounding of values in [-1, 2]
+    assert err <= 1.2e-2, err  # f16 rounding of values in [-1, 2]
     lo = s1.cpu()
     mx = lo.amax(dim=(1, 2), keepdim=True)
     renorm = (torch.maximum(lo, mx - 8.0) + 4.0) / 4.0
@@ -403,7 +403,7 @@ def test_lstm_layer(H, B, T):
     for sfx in ("", "_reverse"):
         s = H ** -0.5
         sd[f"bilstm.weight_ih_l0{sfx}"] = (torch.rand(4 * H, d, generator=g) * 2 - 1) * s
-        sd[f"bilstm.weight_hh_l0{sfx}"] = ((torch.rand(4 * H, H, generator=g) * 2 - 1) * s).bfloat16().float()
+        sd[f"bilstm.weight_hh_l0{sfx}"] = ((torch.rand(4 * H, H, generator=g) * 2 - 1) * s).half().float()
         sd[f"bilstm.bias_ih_l0{sfx}"] = (torch.rand(4 * H, generator=g) * 2 - 1) * s
         sd[f"bilstm.bias_hh_l0{sfx}"] = (torch.rand(4 * H, generator=g) * 2 - 1) * s
     x = torch.randn(B, T, d, generator=g)
@@ -414,9 +414,9 @@ def test_lstm_layer(H, B, T):
         gx = x @ sd[f"bilstm.weight_ih_l0{sfx}"].T + sd[f"bilstm.bias_ih_l0{sfx}"] + sd[f"bilstm.bias_hh_l0{sfx}"]
         cols.append(gx.view(B, T, 4, H).permute(0, 1, 3, 2).reshape(B, T, 4 * H))  # [unit][gate]
     gx = torch.cat(cols, dim=-1).contiguous().to(DEV)
-    whh = torch.stack([sd["bilstm.weight_hh_l0"], sd["bilstm.weight_hh_l0_reverse"]]).to(DEV).bfloat16().contiguous()
-    y16 = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    whh = torch.stack([sd["bilstm.weight_hh_l0"], sd["bilstm.weight_hh_l0_reverse"]]).to(DEV).half().contiguous()
+    y16 = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.float16)
     y32 = torch.full((B, T, d), float("nan"), device=DEV)
-    ops.lstm_layer(gx, whh, B, T, H, y_bf16=y16, y_f32=y32)
-    _report("lstm f32", y32, ref.to(DEV), 1.5e-2)  # h_{t-1} enters the recurrent product in bf16
-    _report("lstm bf16", y16, ref.to(DEV), 2e-2)
+    ops.lstm_layer(gx, whh, B, T, H, y_f16=y16, y_f32=y32)
+    _report("lstm f32", y32, ref.to(DEV), 1.5e-2)  # h_{t-1} enters the recurrent product in f16
+    _report("lstm f16", y16, ref.to(DEV), 2e-2)

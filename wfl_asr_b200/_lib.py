@@ -9,7 +9,7 @@ _C = ctypes
 WFL_MAX_SLABS = 128
 
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-OUT_STORE_BF16, OUT_STORE_F32, OUT_ADD_F32, OUT_GLU_BF16 = 0, 1, 2, 3
+OUT_STORE_F16, OUT_STORE_F32, OUT_ADD_F32, OUT_GLU_F16 = 0, 1, 2, 3
 TAG_O, TAG_B, TAG_I, TAG_OTHER = 0, 1, 2, 3
 MERGE_MODES = {"none": 0, "right": 1, "left": 2, "previous": 3}
 
@@ -49,7 +49,7 @@ SIGNATURES = {
     "wfl_gemm": [_C.POINTER(GemmDesc), _P],
     "wfl_attention": [_P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _I64, _I64, _P],
     "wfl_layernorm": [_P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _I32, _P],
-    "wfl_split_bf16": [_P, _I64, _I32, _P, _P],
+    "wfl_split_f16": [_P, _I64, _I32, _P, _P],
     "wfl_broadcast_rows": [_P, _I64, _I32, _I32, _P, _P],
     "wfl_rowdot_sigmoid": [_P, _I64, _I32, _P, _P, _I32, _P, _P],
     "wfl_peak_normalize": [_P, _P, _I32, _P, _I64, _P, _P, _P],

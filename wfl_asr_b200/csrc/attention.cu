@@ -9,7 +9,7 @@
 //               lane quarter split the 64 score columns of a tile (32 each), so 8 softmax warps per CTA keep
 //               4 warps per SM sub-partition busy at 2 CTAs/SM (the single-warp-per-row version was latency bound).
 //   S_j = Q K_j^T           -> TMEM (fp32, double-buffered so S_{j+1} is computed while softmax_j runs)
-//   P_j = 2^(S_j*c - m)     -> bf16, written by the softmax threads into 128B-swizzled smem (A operand)
+//   P_j = 2^(S_j*c - m)     -> f16, written by the softmax threads into 128B-swizzled smem (A operand)
 //   O  += P_j V_j           -> TMEM (fp32, HD columns); V is consumed MN-major straight from its TMA tile.
 // K and V stream through separate TMA rings: K_j is dead once S_j retired, V_j only after O += P_j V_j.
 // Online softmax with lazy rescaling: O and the row sum are rescaled only when the running max grows
@@ -30,7 +30,7 @@ int attention_big_dispatch(const void* qkv, int64_t row_stride, int64_t batch_st
                            int B, int T, int H, int hd, float scale, void* out, int64_t out_row_stride,
                            int64_t out_batch_stride, cudaStream_t stream);  // attention_big.cu
 
-// P (the bf16 probabilities) is handed to the tensor core through TMEM, overlaying the S tile it was computed from
+// P (the f16 probabilities) is handed to the tensor core through TMEM, overlaying the S tile it was computed from
 // (tcgen05.st by the softmax warps, A-from-TMEM MMA).  At hd 64 the kernel was shared-memory-bandwidth bound: per
 // 64-key tile the MMAs read Q 16 KB + K 8 KB + P 16 KB + V 8 KB and the softmax wrote P 16 KB; this removes 32 KB.
 // false = stage P in 128B-swizzled shared memory (A-from-smem MMA).
@@ -193,10 +193,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     // the whole kernel was paced by it, not by MUFU, shared memory or the tensor pipe.  All ordering between the two
     // streams of MMAs already goes through mbarriers (s_full/s_empty, p_full, pv_done).
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, KV_TILE, 0, 0);
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, KV_TILE, 0, 0);
       constexpr int kPvN = HD <= 256 ? HD : HD / 2;  // N per PV instruction (<= 256, whole 64-column boxes)
       static_assert(kPvN % 64 == 0, "PV chunks must be whole 64-column boxes");
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, kPvN, 0, 1);  // B (= V) is MN-major
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, kPvN, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t k_addr0 = smem_u32(k_smem);
       const uint32_t v_addr0 = smem_u32(v_smem);
@@ -213,7 +213,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int k16 = 0; k16 < HD / 16; ++k16) {
           const uint64_t da = umma_smem_desc(q_addr + (k16 >> 2) * (128 * 128) + (k16 & 3) * 32, 16, 1024);
           const uint64_t db = umma_smem_desc(k_addr + (k16 >> 2) * (KV_TILE * 128) + (k16 & 3) * 32, 16, 1024);
-          umma_bf16_ss(tmem_base + sb * KV_TILE, da, db, idesc_qk, k16 > 0 ? 1u : 0u);
+          umma_f16_ss(tmem_base + sb * KV_TILE, da, db, idesc_qk, k16 > 0 ? 1u : 0u);
         }
         umma_commit(&k_empty[stage]);  // K_j is dead once S_j retired: the next K tile may stream in now
         umma_commit(&s_full[sb]);
@@ -238,10 +238,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint32_t acc = (j > 0 || k16 > 0) ? 1u : 0u;
             if constexpr (kPTmem) {
               // A = P from TMEM: 16 keys = 8 packed 32-bit columns per instruction, overlaying S buffer ss
-              umma_bf16_ts(tmem_base + Cfg::kOCol + nn * kPvN, tmem_base + ss * KV_TILE + k16 * 8, db, idesc_pv, acc);
+              umma_f16_ts(tmem_base + Cfg::kOCol + nn * kPvN, tmem_base + ss * KV_TILE + k16 * 8, db, idesc_pv, acc);
             } else {
               const uint64_t da = umma_smem_desc(pa + k16 * 32, 16, 1024);  // A = P: K-major [128 x 128 B]
-              umma_bf16_ss(tmem_base + Cfg::kOCol + nn * kPvN, da, db, idesc_pv, acc);
+              umma_f16_ss(tmem_base + Cfg::kOCol + nn * kPvN, da, db, idesc_pv, acc);
             }
           }
         }
@@ -343,7 +343,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
         }
 
-        // P = 2^(x - m_used) -> bf16 -> swizzled smem; row sum in fp32
+        // P = 2^(x - m_used) -> f16 -> swizzled smem; row sum in fp32
         const float neg_m = -m_used;
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[16];
@@ -358,11 +358,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             e1 = ex2_approx(x[i + 1] + neg_m);
           }
           sum[(i >> 1) & 3] += e0 + e1;
-#ifdef WFL_EXP_TRUNCPACK  // experiment build only: bf16 by truncation on the ALU pipe instead of F2FP
-          pk[i >> 1] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
-#else
-          pk[i >> 1] = pack_bf16(e0, e1);
-#endif
+          pk[i >> 1] = pack_f16(e0, e1);
         }
         if constexpr (kPTmem) {
           // this warp's 32 keys = 16 packed columns of the P tile that overlays S buffer ss (both warps of the pair
@@ -407,7 +403,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
 
-    // ---- epilogue: O / l -> bf16 -> (Q's smem, no longer needed) -> TMA store
+    // ---- epilogue: O / l -> f16 -> (Q's smem, no longer needed) -> TMA store
     // row sums of the two column halves meet in the exchange buffer the LAST tile did not use
     float* xsum = xmax + (((n_kv - 1) & 1) ^ 1) * 2 * 128;
     xsum[ch * 128 + r] = l_sum;
@@ -424,10 +420,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         uint4 u;
-        u.x = pack_bf16(__uint_as_float(o[8 * q4 + 0]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l);
-        u.y = pack_bf16(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l);
-        u.z = pack_bf16(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l);
-        u.w = pack_bf16(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l);
+        u.x = pack_f16(__uint_as_float(o[8 * q4 + 0]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l);
+        u.y = pack_f16(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l);
+        u.z = pack_f16(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l);
+        u.w = pack_f16(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l);
         const int chunk16 = ((c & 63) >> 3) + q4;
         *reinterpret_cast<uint4*>(blk + ((chunk16 ^ (r & 7)) << 4)) = u;
       }
@@ -461,10 +457,10 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
     uint64_t strides[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
     uint32_t box_q[3] = {64, 128, 1};
     uint32_t box_kv[3] = {64, (uint32_t)kKvTile, 1};
-    int rc = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_q,
+    int rc = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, qkv, dims, strides, box_q,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_tensor_map(&mkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_kv,
+    rc = make_tensor_map(&mkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, qkv, dims, strides, box_kv,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -472,7 +468,7 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
     uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)T, (uint64_t)B};
     uint64_t strides[2] = {(uint64_t)out_row_stride * 2, (uint64_t)out_batch_stride * 2};
     uint32_t box[3] = {64, 32, 1};
-    int rc = make_tensor_map(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box,
+    int rc = make_tensor_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }

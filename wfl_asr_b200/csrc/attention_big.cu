@@ -150,9 +150,9 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   } else if (warp == 1 || warp == 2) {
     // ===== MMA issuers: warp 1 issues the score MMAs, warp 2 the PV MMAs (one issuing thread paces the kernel)
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, kBigKv, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, Cfg::kPvN1, 0, 1);
-      constexpr uint32_t idesc_pv2 = umma_idesc_bf16(128, Cfg::kPvN2 > 0 ? Cfg::kPvN2 : 64, 0, 1);
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, kBigKv, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, Cfg::kPvN1, 0, 1);
+      constexpr uint32_t idesc_pv2 = umma_idesc_f16(128, Cfg::kPvN2 > 0 ? Cfg::kPvN2 : 64, 0, 1);
       (void)idesc_pv2;
       const uint32_t qk_addr = smem_u32(qk_smem);
       const uint32_t v_addr0 = smem_u32(v_smem);
@@ -172,7 +172,7 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_smem_desc(qa + k * 32, 16, 1024);
             const uint64_t db = umma_smem_desc(ka + k * 32, 16, 1024);
-            umma_bf16_ss(tmem_base + sb * kBigKv, da, db, idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ss(tmem_base + sb * kBigKv, da, db, idesc_qk, (c > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&qk_empty[qk_stage]);
           if (++qk_stage == kBigQkStages) {
@@ -196,10 +196,10 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           // B = V, MN-major: 64 value columns (128 B) contiguous, 8 kv rows per 1024 B atom (SBO), next 64 columns
           // one box (kBigKv*128 B) further (LBO).
           const uint64_t db = umma_smem_desc(va + k16 * 2048, kBigKv * 128, 1024);
-          umma_bf16_ss(tmem_base + Cfg::kOCol, da, db, idesc_pv, (j > 0 || k16 > 0) ? 1u : 0u);
+          umma_f16_ss(tmem_base + Cfg::kOCol, da, db, idesc_pv, (j > 0 || k16 > 0) ? 1u : 0u);
           if constexpr (Cfg::kPvN2 > 0) {
             const uint64_t db2 = umma_smem_desc(va + (Cfg::kPvN1 / 64) * (kBigKv * 128) + k16 * 2048, kBigKv * 128, 1024);
-            umma_bf16_ss(tmem_base + Cfg::kOCol + Cfg::kPvN1, da, db2, idesc_pv2, (j > 0 || k16 > 0) ? 1u : 0u);
+            umma_f16_ss(tmem_base + Cfg::kOCol + Cfg::kPvN1, da, db2, idesc_pv2, (j > 0 || k16 > 0) ? 1u : 0u);
           }
         }
         umma_commit(&v_empty[stage]);
@@ -278,7 +278,7 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             e1 = kv0 + c + i + 1 < p.T ? e1 : 0.f;
           }
           sum[(i >> 1) & 3] += e0 + e1;
-          pk[i >> 1] = pack_bf16(e0, e1);
+          pk[i >> 1] = pack_f16(e0, e1);
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -296,7 +296,7 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_arrive(&p_full[sb]);
       }
     }
-    // ---- epilogue: O / l -> bf16 -> staging in the (drained) QK ring -> TMA store of this CTA's value columns
+    // ---- epilogue: O / l -> f16 -> staging in the (drained) QK ring -> TMA store of this CTA's value columns
     mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_sum;
@@ -309,10 +309,10 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         uint4 u;
-        u.x = pack_bf16(__uint_as_float(o[8 * q4 + 0]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l);
-        u.y = pack_bf16(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l);
-        u.z = pack_bf16(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l);
-        u.w = pack_bf16(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l);
+        u.x = pack_f16(__uint_as_float(o[8 * q4 + 0]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l);
+        u.y = pack_f16(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l);
+        u.z = pack_f16(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l);
+        u.w = pack_f16(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l);
         const int chunk16 = ((c & 63) >> 3) + q4;
         *reinterpret_cast<uint4*>(blk + ((chunk16 ^ (r & 7)) << 4)) = u;
       }
@@ -346,10 +346,10 @@ static int launch_big(const void* qkv, int64_t row_stride, int64_t batch_stride,
     uint64_t strides[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
     uint32_t box_q[3] = {64, 128, 1};
     uint32_t box_kv[3] = {64, (uint32_t)kBigKv, 1};
-    int rc = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_q,
+    int rc = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, qkv, dims, strides, box_q,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    rc = make_tensor_map(&mkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, strides, box_kv,
+    rc = make_tensor_map(&mkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, qkv, dims, strides, box_kv,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -357,7 +357,7 @@ static int launch_big(const void* qkv, int64_t row_stride, int64_t batch_stride,
     uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)T, (uint64_t)B};
     uint64_t strides[2] = {(uint64_t)out_row_stride * 2, (uint64_t)out_batch_stride * 2};
     uint32_t box[3] = {64, 32, 1};
-    int rc = make_tensor_map(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box,
+    int rc = make_tensor_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }

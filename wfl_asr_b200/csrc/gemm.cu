@@ -3,13 +3,13 @@
 //
 //   acc[b, t, n] = sum_s sum_k A[b, t + shift_s, col_s + k] * W[n, s * slab_k + k]
 //
-// * A tiles (128 rows x 64 bf16) and W tiles (BN rows x 64 bf16) are fetched by TMA into a
+// * A tiles (128 rows x 64 f16) and W tiles (BN rows x 64 f16) are fetched by TMA into a
 //   128B-swizzled smem ring; rows outside [0, a_rows) come back as zeros, which *is* the Conv1d
 //   zero padding (conv taps are K-slabs with a row shift), so no im2col buffer ever exists.
 // * one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered fp32
 //   accumulator in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
 // * 8 epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias/GELU/ReLU/GLU/alpha, stage the result
-//   in swizzled smem and hand it to TMA: plain store (bf16 / fp32) or cp.reduce.async.bulk add into the
+//   in swizzled smem and hand it to TMA: plain store (f16 / fp32) or cp.reduce.async.bulk add into the
 //   fp32 residual stream.  Partial tiles are clipped by the tensor map, not by branches.
 //
 // Reference arithmetic replaced: nn.Linear / nn.Conv1d calls of REF/model.py:9-16,26-38,98,126-142 and
@@ -22,7 +22,7 @@
 namespace wfl {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int BK = 64;  // 64 f16 = one 128-byte swizzle row
 constexpr int kNumThreads = 384;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kNumEpiWarps = 8;
@@ -58,7 +58,7 @@ struct GemmParams {
 // tools/fit_erf.py; max abs error of the resulting erf 2.4e-7 in fp32) -- one MUFU.EX2 per element instead of
 // libdevice erff's branches, so the GELU epilogue keeps pace with the tensor pipe.
 // gelu(v) = v * Phi(v) with Phi(-|v|) = 0.5 erfc(|v|/sqrt2) = 2^(t P(t) - 1), t = min(|v|/sqrt2, 4.3):
-// 6 FMA-pipe ops + one MUFU.EX2, then a sign select.  |error| < 2e-6, far below the bf16 rounding of the result.
+// 6 FMA-pipe ops + one MUFU.EX2, then a sign select.  |error| < 2e-6, far below the f16 rounding of the result.
 __device__ __forceinline__ float fast_gelu(float v) {
   const float t = fminf(fabsf(v) * 0.70710678118654752f, 4.3f);
   float q = WFL_ERF_C5;
@@ -159,7 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -178,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t dw = umma_smem_desc(sw + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, da, dw, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ss(d_tmem, da, dw, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
@@ -197,7 +197,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     uint8_t* my_staging = staging + ew * Cfg::kStagingBufs * kBoxBytes;
     int sbuf = 0;
     int local = 0;
-    constexpr bool kGlu = OUT_MODE == WFL_OUT_GLU_BF16;
+    constexpr bool kGlu = OUT_MODE == WFL_OUT_GLU_F16;
     constexpr bool kF32 = OUT_MODE == WFL_OUT_STORE_F32 || OUT_MODE == WFL_OUT_ADD_F32;
     // columns of the accumulator this warp converts (GLU: value columns; the gate sits BN/2 further)
     constexpr int kColsPerWarp = kGlu ? BN / 4 : BN / 2;
@@ -284,7 +284,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
           sbuf = (sbuf + 1) % Cfg::kStagingBufs;
         } else {
-          // bf16: two 32-column chunks share one 32x128B box (64 bf16 columns)
+          // f16: two 32-column chunks share one 32x128B box (64 f16 columns)
           const int half_box = (c >> 5) & 1;
           uint8_t* buf = my_staging + sbuf * kBoxBytes;
           if (half_box == 0) {
@@ -294,10 +294,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 q4;
-            q4.x = pack_bf16(f[8 * j], f[8 * j + 1]);
-            q4.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-            q4.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-            q4.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+            q4.x = pack_f16(f[8 * j], f[8 * j + 1]);
+            q4.y = pack_f16(f[8 * j + 2], f[8 * j + 3]);
+            q4.z = pack_f16(f[8 * j + 4], f[8 * j + 5]);
+            q4.w = pack_f16(f[8 * j + 6], f[8 * j + 7]);
             const int chunk16 = half_box * 4 + j;
             *reinterpret_cast<uint4*>(buf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = q4;
           }
@@ -374,7 +374,7 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
 
   int bn = d->tile_n;
   if (bn == 0) {
-    if (d->out_mode == WFL_OUT_GLU_BF16) {
+    if (d->out_mode == WFL_OUT_GLU_F16) {
       bn = 256;
     } else {
       // wave quantisation: the persistent grid runs ceil(tiles / SMs) rounds; pick the tile width whose last round
@@ -389,7 +389,7 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
     }
   }
   WFL_CHECK_ARG(bn == 128 || bn == 256, "wfl_gemm: tile_n must be 0, 128 or 256");
-  if (d->out_mode == WFL_OUT_GLU_BF16)
+  if (d->out_mode == WFL_OUT_GLU_F16)
     WFL_CHECK_ARG(d->n % bn == 0, "wfl_gemm: GLU needs n %% tile_n == 0 (weights are packed per tile)");
 
   CUtensorMap ma, mw, mo;
@@ -398,7 +398,7 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
     uint64_t strides[2] = {(uint64_t)d->a_row_stride * 2, (uint64_t)d->a_batch_stride * 2};
     if (d->batches == 1) strides[1] = (uint64_t)d->a_row_stride * 2 * (uint64_t)d->a_rows;
     uint32_t box[3] = {BK, BM, 1};
-    int rc = make_tensor_map(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d->a, dims, strides, box,
+    int rc = make_tensor_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, d->a, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -406,17 +406,17 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
     uint64_t dims[2] = {(uint64_t)d->num_slabs * d->slab_k, (uint64_t)d->n};
     uint64_t strides[1] = {(uint64_t)d->num_slabs * d->slab_k * 2};
     uint32_t box[2] = {BK, (uint32_t)bn};
-    int rc = make_tensor_map(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->w, dims, strides, box,
+    int rc = make_tensor_map(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->w, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
-    const int out_cols = d->out_mode == WFL_OUT_GLU_BF16 ? d->n / 2 : d->n;
+    const int out_cols = d->out_mode == WFL_OUT_GLU_F16 ? d->n / 2 : d->n;
     uint64_t dims[3] = {(uint64_t)out_cols, (uint64_t)d->m_rows, (uint64_t)d->batches};
     uint64_t strides[2] = {(uint64_t)d->out_row_stride * esz, (uint64_t)d->out_batch_stride * esz};
     if (d->batches == 1) strides[1] = (uint64_t)d->out_row_stride * esz * (uint64_t)d->m_rows;
     uint32_t box[3] = {(uint32_t)(f32_out ? 32 : 64), 32, 1};
-    int rc = make_tensor_map(&mo, f32_out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+    int rc = make_tensor_map(&mo, f32_out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
                              d->out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -440,17 +440,17 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
 #define WFL_LAUNCH(BN_, MODE_) return launch<BN_, MODE_>(ma, mw, mo, p, stream)
   if (bn == 256) {
     switch (d->out_mode) {
-      case WFL_OUT_STORE_BF16: WFL_LAUNCH(256, WFL_OUT_STORE_BF16);
+      case WFL_OUT_STORE_F16: WFL_LAUNCH(256, WFL_OUT_STORE_F16);
       case WFL_OUT_STORE_F32: WFL_LAUNCH(256, WFL_OUT_STORE_F32);
       case WFL_OUT_ADD_F32: WFL_LAUNCH(256, WFL_OUT_ADD_F32);
-      default: WFL_LAUNCH(256, WFL_OUT_GLU_BF16);
+      default: WFL_LAUNCH(256, WFL_OUT_GLU_F16);
     }
   } else {
     switch (d->out_mode) {
-      case WFL_OUT_STORE_BF16: WFL_LAUNCH(128, WFL_OUT_STORE_BF16);
+      case WFL_OUT_STORE_F16: WFL_LAUNCH(128, WFL_OUT_STORE_F16);
       case WFL_OUT_STORE_F32: WFL_LAUNCH(128, WFL_OUT_STORE_F32);
       case WFL_OUT_ADD_F32: WFL_LAUNCH(128, WFL_OUT_ADD_F32);
-      default: WFL_LAUNCH(128, WFL_OUT_GLU_BF16);
+      default: WFL_LAUNCH(128, WFL_OUT_GLU_F16);
     }
   }
 #undef WFL_LAUNCH

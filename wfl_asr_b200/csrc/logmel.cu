@@ -9,13 +9,13 @@
 // The windowed DFT is a dense contraction [3000 x 400] x [400 x 402] per clip and runs on the tensor cores
 // through the slab GEMM of gemm.cu -- without materialising frames: the A operand is a tensor map over the
 // padded waveform whose rows OVERLAP (row stride = hop = 160 samples, row length 400).
-// Precision: a log over 80 dB of dynamic range cannot take bf16 operands as they are (noise floor -54 dB), so
-// both operands are split hi + mid (x = bf16(x) + bf16(x - bf16(x)), ~16 mantissa bits) and three K-slabs
+// Precision: a log over 80 dB of dynamic range cannot take f16 operands as they are (noise floor -54 dB), so
+// both operands are split hi + mid (x = f16(x) + f16(x - f16(x)), ~16 mantissa bits) and three K-slabs
 // accumulate  hi*hi + hi*mid + mid*hi  in fp32 (max feature error vs fp32 FFT ~1e-5, tests/test_ops_gpu.py).
 // The two planes sit 3003 rows apart in the same strided view, so "plane" is just a slab row shift.
-//   1. logmel_prep_kernel : wave fp32 -> reflect-padded bf16 planes [B][2][480480]
+//   1. logmel_prep_kernel : wave fp32 -> reflect-padded f16 planes [B][2][480480]
 //   2. wfl_gemm           : planes x basis[448][3*448] -> X fp32 [B][3000][448] (cos/-sin interleaved per bin)
-//   3. logmel_post_kernel : |X|^2 -> mel -> log10 -> scratch + per-clip max;  4. logmel_finish_kernel -> bf16
+//   3. logmel_post_kernel : |X|^2 -> mel -> log10 -> scratch + per-clip max;  4. logmel_finish_kernel -> f16
 #include <algorithm>
 
 #include "common.cuh"
@@ -42,12 +42,12 @@ __device__ __forceinline__ float float_from_key(unsigned k) {
 }
 
 __global__ void __launch_bounds__(256) logmel_prep_kernel(const float* __restrict__ wave, int64_t wave_stride,
-                                                          int n_samples, __nv_bfloat16* __restrict__ planes) {
+                                                          int n_samples, __half* __restrict__ planes) {
   const int b = blockIdx.y;
   const float* w = wave + b * wave_stride;
   const int valid = n_samples < kPadSamples ? n_samples : kPadSamples;
-  __nv_bfloat16* hi = planes + static_cast<int64_t>(b) * 2 * kPlane;
-  __nv_bfloat16* mid = hi + kPlane;
+  __half* hi = planes + static_cast<int64_t>(b) * 2 * kPlane;
+  __half* mid = hi + kPlane;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kPlane; i += gridDim.x * blockDim.x) {
     float x = 0.f;
     if (i < kPadSamples + kNfft) {
@@ -56,9 +56,9 @@ __global__ void __launch_bounds__(256) logmel_prep_kernel(const float* __restric
       if (j >= kPadSamples) j = 2 * (kPadSamples - 1) - j;
       x = j < valid ? w[j] : 0.f;
     }
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __half h = to_f16(x);
     hi[i] = h;
-    mid[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    mid[i] = to_f16(x - __half2float(h));
   }
 }
 
@@ -123,7 +123,7 @@ logmel_post_kernel(const float* __restrict__ dft /*[B][3000][448]*/, const float
 
 __global__ void __launch_bounds__(256) logmel_finish_kernel(const float* __restrict__ logspec,
                                                             const unsigned* __restrict__ clip_max_key, int n_mels,
-                                                            __nv_bfloat16* __restrict__ out, int out_stride,
+                                                            __half* __restrict__ out, int out_stride,
                                                             int64_t total_rows) {
   const int pairs = out_stride >> 1;
   const int64_t total = total_rows * pairs;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) logmel_finish_kernel(const float* __restr
     float v0 = 0.f, v1 = 0.f;
     if (c < n_mels) v0 = (fmaxf(logspec[row * n_mels + c], floor_v) + 4.0f) / 4.0f;
     if (c + 1 < n_mels) v1 = (fmaxf(logspec[row * n_mels + c + 1], floor_v) + 4.0f) / 4.0f;
-    reinterpret_cast<uint32_t*>(out + row * out_stride)[c >> 1] = pack_bf16(v0, v1);
+    reinterpret_cast<uint32_t*>(out + row * out_stride)[c >> 1] = pack_f16(v0, v1);
   }
 }
 
@@ -147,11 +147,11 @@ constexpr int kPostSmem = kFrameTile * kPwStride * 4;
 using namespace wfl;
 
 extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B,
-                                  const void* basis_split_bf16, const float* mel_filters, int32_t n_mels,
-                                  void* out_bf16, int32_t out_stride, void* scratch_planes, float* scratch_dft,
+                                  const void* basis_split_f16, const float* mel_filters, int32_t n_mels,
+                                  void* out_f16, int32_t out_stride, void* scratch_planes, float* scratch_dft,
                                   float* scratch_logspec, float* scratch_max, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  WFL_CHECK_ARG(wave && basis_split_bf16 && mel_filters && out_bf16 && scratch_planes && scratch_dft &&
+  WFL_CHECK_ARG(wave && basis_split_f16 && mel_filters && out_f16 && scratch_planes && scratch_dft &&
                     scratch_logspec && scratch_max,
                 "wfl_whisper_logmel: null pointer");
   WFL_CHECK_ARG(n_mels == 80 || n_mels == 128, "wfl_whisper_logmel: n_mels must be 80 or 128 (got %d)", n_mels);
@@ -168,7 +168,7 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
   {
     dim3 grid(128, B);
     logmel_prep_kernel<<<grid, 256, 0, stream>>>(wave, wave_stride, n_samples,
-                                                 static_cast<__nv_bfloat16*>(scratch_planes));
+                                                 static_cast<__half*>(scratch_planes));
     WFL_CUDA(cudaGetLastError());
   }
   {
@@ -180,7 +180,7 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
     d.a_row_stride = kHop;
     d.a_batch_stride = 2 * static_cast<int64_t>(kPlane);
     d.batches = B;
-    d.w = basis_split_bf16;
+    d.w = basis_split_f16;
     d.n = kDftCols;
     d.slab_k = kDftCols;
     d.num_slabs = 3;
@@ -209,7 +209,7 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
   const int64_t total = rows * (out_stride / 2);
   const unsigned g2 = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16));
   logmel_finish_kernel<<<g2, 256, 0, stream>>>(scratch_logspec, reinterpret_cast<const unsigned*>(scratch_max), n_mels,
-                                               static_cast<__nv_bfloat16*>(out_bf16), out_stride, rows);
+                                               static_cast<__half*>(out_f16), out_stride, rows);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }

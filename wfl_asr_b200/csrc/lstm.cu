@@ -5,11 +5,11 @@
 // GEMM (gemm.cu) for all time steps; this kernel runs the T strictly serial steps
 //     a_t = gx_t + W_hh h_{t-1};  c_t = s(f) c_{t-1} + s(i) tanh(g);  h_t = s(o) tanh(c_t)
 // One cluster of 8 CTAs owns one direction for a group of 8 batch items:
-//   * W_hh (bf16) never leaves the register file: CTA r holds the 4 gate rows of hidden units
+//   * W_hh (f16) never leaves the register file: CTA r holds the 4 gate rows of hidden units
 //     [r*H/8, (r+1)*H/8) as mma.sync m16n8k16 A-fragments, split over (unit group) x (K half) warps.
 //     Row tiles are arranged (i|f) and (g|o) per 8 units, so one thread ends up with all four gate
 //     pre-activations of its (unit, batch) cells and the cell update needs no data exchange.
-//   * h_{t-1} (bf16, [batch][H]) lives in shared memory of every CTA, double buffered; after the cell
+//   * h_{t-1} (f16, [batch][H]) lives in shared memory of every CTA, double buffered; after the cell
 //     update each CTA pushes its H/8 slice to all 8 CTAs with 16-byte DSMEM stores and the cluster
 //     meets at one barrier.cluster per step.  c_t stays in fp32 registers for the whole sequence.
 //   * gx_t is prefetched one step ahead as float4 (columns are packed [dir][unit][gate]).
@@ -20,9 +20,9 @@ namespace wfl {
 
 constexpr int kLstmNB = 8;  // batch items per cluster = one n8 MMA tile
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -39,7 +39,7 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-// MUFU.EX2 + MUFU.RCP based, ~1e-6 absolute error (the recurrent operand h is rounded to bf16 anyway)
+// MUFU.EX2 + MUFU.RCP based, ~1e-6 absolute error (the recurrent operand h is rounded to f16 anyway)
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_acc(float x) {
   // tanh(x) = 1 - 2 / (1 + e^{2x}); saturates cleanly for large |x| (e = inf -> 1, e = 0 -> -1)
@@ -59,7 +59,7 @@ struct LstmCfg {
   static constexpr int kKTiles = H / 16 / kKSplit;  // k16 tiles per warp
   static constexpr int kHStride = H + 8;            // padded row (bank-conflict-free B fragments)
   static constexpr int kHBufBytes = 2 * kLstmNB * kHStride * 2;
-  static constexpr int kStageBytes = kLstmNB * kUnits * 2;  // this CTA's h slice, [n][unit] bf16
+  static constexpr int kStageBytes = kLstmNB * kUnits * 2;  // this CTA's h slice, [n][unit] f16
   static constexpr int kPartBytes = kGroups * 32 * 8 * 4;   // K-half partial sums
   static constexpr int kVecPerRow = kUnits * 2 / 16;        // 16-byte vectors per (n) row of the slice
   static_assert(H % (CL * 8) == 0, "H must be a multiple of 8 * cluster size");
@@ -68,15 +68,15 @@ struct LstmCfg {
 
 template <int H, int CL>
 __global__ void __launch_bounds__((LstmCfg<H, CL>::kThreads), 1)
-lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh, int B, int T,
-            __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32) {
+lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B, int T,
+            __half* __restrict__ y_f16, float* __restrict__ y_f32) {
   using Cfg = LstmCfg<H, CL>;
   constexpr int kLstmCluster = CL;
   __shared__ __align__(16) uint8_t hbuf_raw[Cfg::kHBufBytes];
   __shared__ __align__(16) uint8_t stage_raw[Cfg::kStageBytes];
   __shared__ __align__(16) float part[Cfg::kGroups * 32 * 8];
-  __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(hbuf_raw);  // [2][NB][kHStride]
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(stage_raw);
+  __half* hbuf = reinterpret_cast<__half*>(hbuf_raw);  // [2][NB][kHStride]
+  __half* stage = reinterpret_cast<__half*>(stage_raw);
 
   const int rank = blockIdx.x;  // == %cluster_ctarank (cluster spans gridDim.x)
   const int b0 = blockIdx.y * kLstmNB;
@@ -92,7 +92,7 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
   // ---- W_hh fragments -> registers (kept for all T steps)
   uint32_t wa[Cfg::kKTiles][4], wb[Cfg::kKTiles][4];
   {
-    const __nv_bfloat16* w = whh + static_cast<int64_t>(dir) * 4 * H * H;
+    const __half* w = whh + static_cast<int64_t>(dir) * 4 * H * H;
     const uint32_t* wi = reinterpret_cast<const uint32_t*>(w + static_cast<int64_t>(0 * H + unit) * H);
     const uint32_t* wf = reinterpret_cast<const uint32_t*>(w + static_cast<int64_t>(1 * H + unit) * H);
     const uint32_t* wg = reinterpret_cast<const uint32_t*>(w + static_cast<int64_t>(2 * H + unit) * H);
@@ -134,17 +134,17 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
     // four independent accumulator chains (even / odd k-tiles) halve the dependent-MMA latency chain
     float acc_if[4] = {0.f, 0.f, 0.f, 0.f}, acc_go[4] = {0.f, 0.f, 0.f, 0.f};
     float acc_if2[4] = {0.f, 0.f, 0.f, 0.f}, acc_go2[4] = {0.f, 0.f, 0.f, 0.f};
-    const __nv_bfloat16* hrow = hbuf + (cur * kLstmNB + g) * Cfg::kHStride + khalf * Cfg::kKTiles * 16 + 2 * q;
+    const __half* hrow = hbuf + (cur * kLstmNB + g) * Cfg::kHStride + khalf * Cfg::kKTiles * 16 + 2 * q;
 #pragma unroll
     for (int kt = 0; kt < Cfg::kKTiles; ++kt) {
       const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16);
       const uint32_t hb1 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16 + 8);
       if (kt & 1) {
-        mma_bf16_16816(acc_if2, wa[kt], hb0, hb1);
-        mma_bf16_16816(acc_go2, wb[kt], hb0, hb1);
+        mma_f16_16816(acc_if2, wa[kt], hb0, hb1);
+        mma_f16_16816(acc_go2, wb[kt], hb0, hb1);
       } else {
-        mma_bf16_16816(acc_if, wa[kt], hb0, hb1);
-        mma_bf16_16816(acc_go, wb[kt], hb0, hb1);
+        mma_f16_16816(acc_if, wa[kt], hb0, hb1);
+        mma_f16_16816(acc_go, wb[kt], hb0, hb1);
       }
     }
 #pragma unroll
@@ -180,15 +180,15 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
       const float h0 = sigmoid_acc(ao0) * tanh_acc(c_state[0]);
       const float h1 = sigmoid_acc(ao1) * tanh_acc(c_state[1]);
       const int ul = group * 8 + g;  // unit inside this CTA's slice
-      stage[(2 * q) * Cfg::kUnits + ul] = __float2bfloat16_rn(h0);
-      stage[(2 * q + 1) * Cfg::kUnits + ul] = __float2bfloat16_rn(h1);
+      stage[(2 * q) * Cfg::kUnits + ul] = to_f16(h0);
+      stage[(2 * q + 1) * Cfg::kUnits + ul] = to_f16(h1);
       if (y_f32 != nullptr) {
         if (bq0 < B) y_f32[(static_cast<int64_t>(bq0) * T + t) * (2 * H) + dir * H + unit] = h0;
         if (bq1 < B) y_f32[(static_cast<int64_t>(bq1) * T + t) * (2 * H) + dir * H + unit] = h1;
       }
     }
     __syncthreads();
-    // ---- push this CTA's slice of h_t to every CTA of the cluster (and to global as bf16)
+    // ---- push this CTA's slice of h_t to every CTA of the cluster (and to global as f16)
     constexpr int kVecs = kLstmCluster * kLstmNB * Cfg::kVecPerRow;
     for (int i = threadIdx.x; i < kVecs; i += Cfg::kThreads) {
       const int dst = i / (kLstmNB * Cfg::kVecPerRow);
@@ -199,12 +199,12 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
       const uint32_t off = ((nxt * kLstmNB + n) * Cfg::kHStride + rank * Cfg::kUnits) * 2 + v * 16;
       st_cluster_v4(map_to_cta(hbuf_local + off, dst), val);
     }
-    if (y_bf16 != nullptr) {
+    if (y_f16 != nullptr) {
       for (int i = threadIdx.x; i < kLstmNB * Cfg::kVecPerRow; i += Cfg::kThreads) {
         const int n = i / Cfg::kVecPerRow, v = i - n * Cfg::kVecPerRow;
         if (b0 + n < B) {
           const uint4 val = *reinterpret_cast<const uint4*>(stage_raw + (n * Cfg::kUnits) * 2 + v * 16);
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y_bf16) +
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y_f16) +
                                     ((static_cast<int64_t>(b0 + n) * T + t) * (2 * H) + dir * H + rank * Cfg::kUnits) * 2 +
                                     v * 16) = val;
         }
@@ -215,7 +215,7 @@ lstm_kernel(const float* __restrict__ gx, const __nv_bfloat16* __restrict__ whh,
 }
 
 template <int H, int CL>
-static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_bf16, float* y_f32, cudaStream_t stream) {
+static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_f16, float* y_f32, cudaStream_t stream) {
   using Cfg = LstmCfg<H, CL>;
   constexpr int kLstmCluster = CL;
   if (CL > 8) {
@@ -237,25 +237,25 @@ static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_b
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  WFL_CUDA(cudaLaunchKernelEx(&cfg, lstm_kernel<H, CL>, gx, static_cast<const __nv_bfloat16*>(whh), B, T,
-                              static_cast<__nv_bfloat16*>(y_bf16), y_f32));
+  WFL_CUDA(cudaLaunchKernelEx(&cfg, lstm_kernel<H, CL>, gx, static_cast<const __half*>(whh), B, T,
+                              static_cast<__half*>(y_f16), y_f32));
   return WFL_OK;
 }
 
 }  // namespace wfl
 
-extern "C" int wfl_lstm_layer(const float* gx, const void* whh_bf16, int32_t B, int32_t T, int32_t H, void* y_bf16,
+extern "C" int wfl_lstm_layer(const float* gx, const void* whh_f16, int32_t B, int32_t T, int32_t H, void* y_f16,
                               float* y_f32, void* stream_) {
   using namespace wfl;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  WFL_CHECK_ARG(gx && whh_bf16 && (y_bf16 || y_f32), "wfl_lstm_layer: null pointer");
+  WFL_CHECK_ARG(gx && whh_f16 && (y_f16 || y_f32), "wfl_lstm_layer: null pointer");
   WFL_CHECK_ARG(B >= 1 && T >= 1, "wfl_lstm_layer: empty problem");
   switch (H) {
-    case 192: return launch_lstm<192, 8>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
-    case 256: return launch_lstm<256, 8>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
-    case 384: return launch_lstm<384, 8>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
-    case 512: return launch_lstm<512, 16>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
-    case 640: return launch_lstm<640, 16>(gx, whh_bf16, B, T, y_bf16, y_f32, stream);
+    case 192: return launch_lstm<192, 8>(gx, whh_f16, B, T, y_f16, y_f32, stream);
+    case 256: return launch_lstm<256, 8>(gx, whh_f16, B, T, y_f16, y_f32, stream);
+    case 384: return launch_lstm<384, 8>(gx, whh_f16, B, T, y_f16, y_f32, stream);
+    case 512: return launch_lstm<512, 16>(gx, whh_f16, B, T, y_f16, y_f32, stream);
+    case 640: return launch_lstm<640, 16>(gx, whh_f16, B, T, y_f16, y_f32, stream);
     default:
       set_error("wfl_lstm_layer: hidden size %d not built (supported: 192, 256, 384, 512, 640)", H);
       return WFL_ERR_UNSUPPORTED;

@@ -1,4 +1,4 @@
-// Memory-bound row kernels of the labeling path (K0, K8 and small glue): LayerNorm, hi/lo bf16
+// Memory-bound row kernels of the labeling path (K0, K8 and small glue): LayerNorm, hi/lo f16
 // split, positional-embedding broadcast, offset-head row dot + sigmoid, peak normalisation.
 // All use 128-bit loads/stores and warp shuffles; one warp owns one row.
 #include <algorithm>
@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma2,
                                                         const float* __restrict__ beta2, float eps,
                                                         float* __restrict__ out_f32,
-                                                        __nv_bfloat16* __restrict__ out_bf16, int act) {
+                                                        __half* __restrict__ out_f16, int act) {
   pdl_launch_dependents();  // the GEMM that consumes this output may run its prologue while these rows finish
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       v[i].z = (v[i].z - mean) * rstd * g.z + b.z;
       v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
       if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * d)[idx] = v[i];
-      if (act == WFL_ACT_GELU) {  // bf16 branch only: act(LN(x)), optionally followed by the second LayerNorm
+      if (act == WFL_ACT_GELU) {  // f16 branch only: act(LN(x)), optionally followed by the second LayerNorm
         v[i].x = gelu_erf(v[i].x);
         v[i].y = gelu_erf(v[i].y);
         v[i].z = gelu_erf(v[i].z);
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  if (out_bf16 == nullptr) return;
+  if (out_f16 == nullptr) return;
   if (gamma2 != nullptr) {
     mean = warp_sum(s) * inv_d;
     q = 0.f;
@@ -95,32 +95,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       }
     }
   }
-  uint2* orow = reinterpret_cast<uint2*>(out_bf16 + row * d);
+  uint2* orow = reinterpret_cast<uint2*>(out_f16 + row * d);
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int idx = lane + i * 32;
-    if (idx < nvec) orow[idx] = make_uint2(pack_bf16(v[i].x, v[i].y), pack_bf16(v[i].z, v[i].w));
+    if (idx < nvec) orow[idx] = make_uint2(pack_f16(v[i].x, v[i].y), pack_f16(v[i].z, v[i].w));
   }
 }
 
-__global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restrict__ x, int64_t rows, int d4,
-                                                         __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256) split_f16_kernel(const float4* __restrict__ x, int64_t rows, int d4,
+                                                         __half* __restrict__ out) {
   const int64_t total = rows * d4;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / d4;
     const int c = static_cast<int>(i - r * d4);
     const float4 v = x[i];
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                        h3 = __float2bfloat16_rn(v.w);
-    const float l0 = v.x - __bfloat162float(h0), l1 = v.y - __bfloat162float(h1), l2 = v.z - __bfloat162float(h2),
-                l3 = v.w - __bfloat162float(h3);
-    __nv_bfloat16* orow = out + r * (8 * static_cast<int64_t>(d4));
+    const __half h0 = to_f16(v.x), h1 = to_f16(v.y), h2 = to_f16(v.z),
+                        h3 = to_f16(v.w);
+    const float l0 = v.x - __half2float(h0), l1 = v.y - __half2float(h1), l2 = v.z - __half2float(h2),
+                l3 = v.w - __half2float(h3);
+    __half* orow = out + r * (8 * static_cast<int64_t>(d4));
     uint2 hi, lo;
-    hi.x = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
-    hi.y = pack_bf16(__bfloat162float(h2), __bfloat162float(h3));
-    lo.x = pack_bf16(l0, l1);
-    lo.y = pack_bf16(l2, l3);
+    hi.x = pack_f16(__half2float(h0), __half2float(h1));
+    hi.y = pack_f16(__half2float(h2), __half2float(h3));
+    lo.x = pack_f16(l0, l1);
+    lo.y = pack_f16(l2, l3);
     reinterpret_cast<uint2*>(orow)[c] = hi;
     reinterpret_cast<uint2*>(orow + 4 * static_cast<int64_t>(d4))[c] = lo;
   }
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) broadcast_rows_kernel(const float4* __res
 }
 
 // Offset head tail (REF/model.py:140-141): out[r][j] = sigmoid(x[r] . w[j] + b[j]); one warp per row.
-__global__ void __launch_bounds__(256) rowdot_sigmoid_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int d,
+__global__ void __launch_bounds__(256) rowdot_sigmoid_kernel(const __half* __restrict__ x, int64_t rows, int d,
                                                              const float* __restrict__ w,
                                                              const float* __restrict__ bias, int n_out,
                                                              float* __restrict__ out) {
@@ -151,8 +151,9 @@ __global__ void __launch_bounds__(256) rowdot_sigmoid_kernel(const __nv_bfloat16
     float xv[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      xv[2 * k] = __uint_as_float(uu[k] << 16);
-      xv[2 * k + 1] = __uint_as_float(uu[k] & 0xffff0000u);
+      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&uu[k]));
+      xv[2 * k] = f2.x;
+      xv[2 * k + 1] = f2.y;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -214,11 +215,11 @@ __global__ void __launch_bounds__(256) peak_scale_kernel(const double* __restric
 using namespace wfl;
 
 extern "C" int wfl_layernorm(const float* x, int64_t rows, int32_t d, const float* gamma, const float* beta,
-                             const float* gamma2, const float* beta2, float eps, float* out_f32, void* out_bf16,
-                             int32_t act_bf16, void* stream) {
+                             const float* gamma2, const float* beta2, float eps, float* out_f32, void* out_f16,
+                             int32_t act_f16, void* stream) {
   WFL_CHECK_ARG(x && gamma && beta, "wfl_layernorm: null input");
-  WFL_CHECK_ARG(act_bf16 == WFL_ACT_NONE || act_bf16 == WFL_ACT_GELU, "wfl_layernorm: act_bf16 must be NONE or GELU");
-  WFL_CHECK_ARG(out_f32 || out_bf16, "wfl_layernorm: no output requested");
+  WFL_CHECK_ARG(act_f16 == WFL_ACT_NONE || act_f16 == WFL_ACT_GELU, "wfl_layernorm: act_f16 must be NONE or GELU");
+  WFL_CHECK_ARG(out_f32 || out_f16, "wfl_layernorm: no output requested");
   WFL_CHECK_ARG(d > 0 && d % 4 == 0 && d <= kLnMaxVecLimit * 128, "wfl_layernorm: d=%d must be a multiple of 4, <= %d", d,
                 kLnMaxVecLimit * 128);
   WFL_CHECK_ARG((gamma2 == nullptr) == (beta2 == nullptr), "wfl_layernorm: gamma2/beta2 must come together");
@@ -226,27 +227,27 @@ extern "C" int wfl_layernorm(const float* x, int64_t rows, int32_t d, const floa
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   // registers scale with the per-lane vector count, so pick the smallest instantiation (occupancy = bytes in flight)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  __half* ob = static_cast<__half*>(out_f16);
   if (d <= 512)
-    layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
+    layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   else if (d <= 768)
-    layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
+    layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   else if (d <= 1024)
-    layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
+    layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   else
-    layernorm_kernel<12><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_bf16);
+    layernorm_kernel<12><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }
 
-extern "C" int wfl_split_bf16(const float* x, int64_t rows, int32_t d, void* out_hi_lo, void* stream) {
-  WFL_CHECK_ARG(x && out_hi_lo, "wfl_split_bf16: null pointer");
-  WFL_CHECK_ARG(d > 0 && d % 4 == 0, "wfl_split_bf16: d must be a multiple of 4");
+extern "C" int wfl_split_f16(const float* x, int64_t rows, int32_t d, void* out_hi_lo, void* stream) {
+  WFL_CHECK_ARG(x && out_hi_lo, "wfl_split_f16: null pointer");
+  WFL_CHECK_ARG(d > 0 && d % 4 == 0, "wfl_split_f16: d must be a multiple of 4");
   if (rows <= 0) return WFL_OK;
   const int64_t total = rows * (d / 4);
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16));
-  split_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x), rows, d / 4,
-                                                                        static_cast<__nv_bfloat16*>(out_hi_lo));
+  split_f16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x), rows, d / 4,
+                                                                        static_cast<__half*>(out_hi_lo));
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }
@@ -264,14 +265,14 @@ extern "C" int wfl_broadcast_rows(const float* src, int64_t rows, int32_t d, int
   return WFL_OK;
 }
 
-extern "C" int wfl_rowdot_sigmoid(const void* x_bf16, int64_t rows, int32_t d, const float* w, const float* b,
+extern "C" int wfl_rowdot_sigmoid(const void* x_f16, int64_t rows, int32_t d, const float* w, const float* b,
                                   int32_t n_out, float* out, void* stream) {
-  WFL_CHECK_ARG(x_bf16 && w && b && out, "wfl_rowdot_sigmoid: null pointer");
+  WFL_CHECK_ARG(x_f16 && w && b && out, "wfl_rowdot_sigmoid: null pointer");
   WFL_CHECK_ARG(d > 0 && d % 8 == 0 && n_out >= 1 && n_out <= 4, "wfl_rowdot_sigmoid: bad shape");
   if (rows <= 0) return WFL_OK;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   rowdot_sigmoid_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x_bf16), rows, d, w, b, n_out, out);
+      static_cast<const __half*>(x_f16), rows, d, w, b, n_out, out);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }

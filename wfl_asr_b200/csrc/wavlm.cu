@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
 }
 
 // mode 0: accumulate per-(clip, channel) sum / sumsq of the conv output (GroupNorm statistics)
-// mode 1: GroupNorm apply (per-channel statistics over time) + GELU -> bf16
-// mode 2: LayerNorm over the 512 channels of each frame + GELU -> bf16
+// mode 1: GroupNorm apply (per-channel statistics over time) + GELU -> f16
+// mode 2: LayerNorm over the 512 channels of each frame + GELU -> f16
 // Thread c (of 512) owns channel c: its 10 taps live in registers; the waveform window is staged in smem.
 template <int MODE>
 __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wave, int64_t wave_stride, int n_samples,
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wa
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     const double* __restrict__ clip_stats, int normalize_input,
                                                     double* __restrict__ ch_stats /*[B][512][2]*/,
-                                                    __nv_bfloat16* __restrict__ out, int64_t out_batch_stride) {
+                                                    __half* __restrict__ out, int64_t out_batch_stride) {
   __shared__ float xs[kC0Frames * kC0Stride + kC0Taps];
   __shared__ float red[2][16];
   const int b = blockIdx.y;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wa
       q_acc = fmaf(y, y, q_acc);
     } else if (MODE == 1) {
       const float v = (y - mean_c) * rstd_c * ga + be;
-      out[b * out_batch_stride + static_cast<int64_t>(t0 + f) * kC0 + c] = __float2bfloat16_rn(gelu_exact(v));
+      out[b * out_batch_stride + static_cast<int64_t>(t0 + f) * kC0 + c] = to_f16(gelu_exact(v));
     } else {
       // LayerNorm over channels: block-wide mean / variance of y for this frame
       float s1 = warp_sum(y);
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wa
 #pragma unroll
       for (int i = 0; i < 16; ++i) tv += red[1][i];
       const float v = dlt * (1.0f / sqrtf(tv * (1.0f / kC0) + 1e-5f)) * ga + be;
-      out[b * out_batch_stride + static_cast<int64_t>(t0 + f) * kC0 + c] = __float2bfloat16_rn(gelu_exact(v));
+      out[b * out_batch_stride + static_cast<int64_t>(t0 + f) * kC0 + c] = to_f16(gelu_exact(v));
     }
   }
   if (MODE == 0) {
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wa
 
 // K10: gate[b][h][t] = ga * (gb * const[h] - 1) + 2 with (ga, gb) = sigmoid(sum4(Linear(hd -> 8)(x[b,t,h*hd:(h+1)*hd])))
 // one warp per (row, head): hd = 64 -> 2 elements per lane.
-__global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __restrict__ x, int64_t row_stride, int B,
+__global__ void __launch_bounds__(256) wavlm_gate_kernel(const __half* __restrict__ x, int64_t row_stride, int B,
                                                          int T, int Hh, int hd, const float* __restrict__ gw /*[8][hd]*/,
                                                          const float* __restrict__ gb /*[8]*/,
                                                          const float* __restrict__ gconst /*[H]*/,
@@ -151,10 +151,10 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __
   if (wid >= total) return;
   const int h = static_cast<int>(wid % Hh);
   const int64_t row = wid / Hh;  // b * T + t
-  const __nv_bfloat16* xr = x + row * row_stride + h * hd;
+  const __half* xr = x + row * row_stride + h * hd;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int k = lane; k < hd; k += 32) {
-    const float xv = __bfloat162float(xr[k]);
+    const float xv = __half2float(xr[k]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, __ldg(gw + j * hd + k), acc[j]);
   }
@@ -175,17 +175,17 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __
 using namespace wfl;
 
 extern "C" int wfl_wavlm_conv0(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, const float* w,
-                               const float* gamma, const float* beta, int32_t norm_mode, void* out_bf16,
+                               const float* gamma, const float* beta, int32_t norm_mode, void* out_f16,
                                int64_t out_batch_stride, double* scratch_stats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  WFL_CHECK_ARG(wave && w && gamma && beta && out_bf16 && scratch_stats, "wfl_wavlm_conv0: null pointer");
+  WFL_CHECK_ARG(wave && w && gamma && beta && out_f16 && scratch_stats, "wfl_wavlm_conv0: null pointer");
   WFL_CHECK_ARG(norm_mode == 0 || norm_mode == 1, "wfl_wavlm_conv0: norm_mode must be 0 (group) or 1 (layer)");
   WFL_CHECK_ARG(n_samples >= kC0Taps && wave_stride >= n_samples, "wfl_wavlm_conv0: clip shorter than the 10-tap kernel");
   if (B <= 0) return WFL_OK;
   const int T0 = (n_samples - kC0Taps) / kC0Stride + 1;
   WFL_CHECK_ARG(out_batch_stride >= static_cast<int64_t>(T0) * kC0, "wfl_wavlm_conv0: out_batch_stride too small");
   dim3 grid((T0 + kC0Frames - 1) / kC0Frames, B);
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
+  __half* out = static_cast<__half*>(out_f16);
   double* clip_stats = scratch_stats;            // [B][2]
   double* ch_stats = scratch_stats + 2 * B;      // [B][512][2]
   if (norm_mode == 0) {
@@ -209,14 +209,14 @@ extern "C" int wfl_wavlm_conv0(const float* wave, int64_t wave_stride, int32_t n
   return WFL_OK;
 }
 
-extern "C" int wfl_wavlm_gate(const void* x_bf16, int64_t row_stride, int32_t B, int32_t T, int32_t H, int32_t hd,
+extern "C" int wfl_wavlm_gate(const void* x_f16, int64_t row_stride, int32_t B, int32_t T, int32_t H, int32_t hd,
                               const float* gate_w, const float* gate_b, const float* gate_const, float* gate,
                               void* stream) {
-  WFL_CHECK_ARG(x_bf16 && gate_w && gate_b && gate_const && gate, "wfl_wavlm_gate: null pointer");
+  WFL_CHECK_ARG(x_f16 && gate_w && gate_b && gate_const && gate, "wfl_wavlm_gate: null pointer");
   WFL_CHECK_ARG(B >= 1 && T >= 1 && H >= 1 && hd >= 1, "wfl_wavlm_gate: bad shape");
   const int64_t total = static_cast<int64_t>(B) * T * H;
   wavlm_gate_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x_bf16), row_stride, B, T, H, hd, gate_w, gate_b, gate_const, gate);
+      static_cast<const __half*>(x_f16), row_stride, B, T, H, hd, gate_w, gate_b, gate_const, gate);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }

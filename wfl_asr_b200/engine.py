@@ -3,10 +3,10 @@ sequence of libwfl_b200.so launches on the caller's CUDA stream.
 
 Data layout in HBM (B clips, T frames, d hidden), all row-major with channels last:
   x      fp32 [B, T, d]   residual stream (GEMM epilogues accumulate into it with TMA reduce-add)
-  h, ctx bf16 [B*T, d]    LayerNorm outputs / attention context  (GEMM A operands)
-  qkv    bf16 [B*T, 3d]   packed projections, read in place by the attention kernel
-  u      bf16 [B*T, F]    MLP / GLU intermediates
-  hl     bf16 [B*T, 2d]   [hi | lo] split of the final hidden state for the split-precision tail
+  h, ctx f16 [B*T, d]    LayerNorm outputs / attention context  (GEMM A operands)
+  qkv    f16 [B*T, 3d]   packed projections, read in place by the attention kernel
+  u      f16 [B*T, F]    MLP / GLU intermediates
+  hl     f16 [B*T, 2d]   [hi | lo] split of the final hidden state for the split-precision tail
 Reference call order followed: REF/model.py:148-194 (forward), :40-52 (ConformerBlock),
 TF/models/whisper/modeling_whisper.py:593-647, TF/models/wavlm/modeling_wavlm.py:1039-1095.
 """
@@ -37,10 +37,10 @@ class Engine:
     # ------------------------------------------------------------------------------------ packing
     def _put(self, name, t, dtype=None):
         t = t.to(self.dev)
-        self.W[name] = packing.bf16(t) if dtype == "bf16" else t.detach().float().contiguous()
+        self.W[name] = packing.f16(t) if dtype == "f16" else t.detach().float().contiguous()
 
     def _pack_linear(self, name, w, b):
-        self._put(name + ".w", w, "bf16")
+        self._put(name + ".w", w, "f16")
         if b is not None:
             self._put(name + ".b", b)
 
@@ -56,7 +56,7 @@ class Engine:
             self._pack_wavlm(sd)
         # lang conditioning (REF/model.py:176-180): W [d, d+E] -> W_h and a per-language bias
         w = sd["lang_proj.weight"].float()
-        self._put("lang.w", w[:, :d], "bf16")
+        self._put("lang.w", w[:, :d], "f16")
         self._put("lang.bias", sd["lang_emb.weight"].float() @ w[:, d:].T + sd["lang_proj.bias"].float())
         if m.get("enable_bilstm", True):
             self._pack_bilstm(sd)
@@ -88,7 +88,7 @@ class Engine:
                               sd[f"dilated_conv_stack.{2 * i}.bias"])
         # classifier in split precision: A = [hi | lo], W = [hi | hi | lo]  (x_hi w_hi + x_lo w_hi + x_hi w_lo)
         wc = packing.pad_rows(sd["classifier.weight"].float(), self.Lp)
-        self._put("cls.w", packing.split_hi_lo(wc))  # already bf16
+        self._put("cls.w", packing.split_hi_lo(wc))  # already f16
         self.W["cls.w"] = packing.split_hi_lo(wc.to(self.dev))
         bc = torch.zeros(self.Lp, device=self.dev)
         bc[:self.L] = sd["classifier.bias"].float().to(self.dev)
@@ -126,7 +126,7 @@ class Engine:
         self._put("wl.c0.w", sd[fe + "0.conv.weight"].float()[:, 0, :])  # [512, 10]
         self._pack_ln("wl.c0.ln", sd, fe + "0.layer_norm")
         for i in range(1, 7):
-            self._put(f"wl.c{i}.w", packing.conv_taps(sd[fe + f"{i}.conv.weight"].float()), "bf16")
+            self._put(f"wl.c{i}.w", packing.conv_taps(sd[fe + f"{i}.conv.weight"].float()), "f16")
             if a["norm"] == "layer":
                 self._pack_ln(f"wl.c{i}.ln", sd, fe + f"{i}.layer_norm")
         self._pack_ln("wl.fp.ln", sd, "encoder.feature_projection.layer_norm")
@@ -143,7 +143,7 @@ class Engine:
             wt = w[gi * cg:(gi + 1) * cg].permute(0, 2, 1)  # [cg out, 128 taps, cg in]
             wp = wt.new_zeros(cg, K, 64)  # each tap is one 64-wide K slab; channels past cg belong to the next group -> 0
             wp[:, :, :cg] = wt
-            self._put(f"wl.pos{gi}.w", wp.reshape(cg, K * 64), "bf16")
+            self._put(f"wl.pos{gi}.w", wp.reshape(cg, K * 64), "f16")
             self._put(f"wl.pos{gi}.b", bias[gi * cg:(gi + 1) * cg])
         self._pack_ln("wl.enc.ln", sd, "encoder.encoder.layer_norm")
         for i in range(a["layers"]):
@@ -197,7 +197,7 @@ class Engine:
                 b_in.append(b.view(4, Hs).t().reshape(-1))
                 w_hh.append(sd[f"bilstm.weight_hh_l{layer}{suffix}"].float())
             self._pack_linear(f"lstm{layer}.in", torch.cat(w_in, 0), torch.cat(b_in, 0))
-            self._put(f"lstm{layer}.whh", torch.stack(w_hh, 0), "bf16")
+            self._put(f"lstm{layer}.whh", torch.stack(w_hh, 0), "f16")
 
     # ------------------------------------------------------------------------------------ workspaces
     def _buffers(self, B, T, n_samples=None):
@@ -207,7 +207,7 @@ class Engine:
             return ws
         d, dev, M = self.d, self.dev, B * T
         F = max(self.arch["ffn"], self.ffx * d, 2 * d)
-        bf = dict(device=dev, dtype=torch.bfloat16)
+        bf = dict(device=dev, dtype=torch.float16)
         ws = {
             "x": torch.empty(B, T, d, device=dev),
             "h": torch.empty(M, d, **bf),
@@ -293,12 +293,12 @@ class Engine:
         hd = d // H
         for i in range(a["layers"]):
             q = f"enc{i}."
-            self._ln(x, q + "ln1", out_bf16=ws["h"])
+            self._ln(x, q + "ln1", out_f16=ws["h"])
             self._linear(ws["h"], q + "qkv", ws["qkv"], M, d)
             ops.attention(ws["qkv"].view(B, T, 3 * d), ws["ctx"].view(B, T, d), B=B, T=T, H=H, hd=hd,
                           scale=hd ** -0.5, q_col=0, k_col=d, v_col=2 * d)
             self._linear(ws["ctx"], q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
-            self._ln(x, q + "ln2", out_bf16=ws["h"])
+            self._ln(x, q + "ln2", out_f16=ws["h"])
             self._linear(ws["h"], q + "fc1", ws["u"], M, d, act=ops.ACT_GELU)
             self._linear(ws["u"], q + "fc2", x, M, a["ffn"], out_mode=ops.OUT_ADD_F32)
         return T
@@ -335,12 +335,12 @@ class Engine:
                 g1, b1 = self.W[f"wl.c{i}.ln.g"], self.W[f"wl.c{i}.ln.b"]
                 if last:  # LayerNorm + GELU, then the feature-projection LayerNorm, in one pass
                     ops.layernorm(ws["cf"], g1, b1, gamma2=self.W["wl.fp.ln.g"], beta2=self.W["wl.fp.ln.b"],
-                                  out_bf16=ws["h512"], act_bf16=ops.ACT_GELU, rows=B * t_out)
+                                  out_f16=ws["h512"], act_f16=ops.ACT_GELU, rows=B * t_out)
                 else:
-                    ops.layernorm(ws["cf"], g1, b1, out_bf16=dst, act_bf16=ops.ACT_GELU, rows=B * t_out)
+                    ops.layernorm(ws["cf"], g1, b1, out_f16=dst, act_f16=ops.ACT_GELU, rows=B * t_out)
             elif last:
                 ops.gemm(src, self.W[f"wl.c{i}.w"], ws["cf"], act=ops.ACT_GELU, out_mode=ops.OUT_STORE_F32, **common)
-                ops.layernorm(ws["cf"], self.W["wl.fp.ln.g"], self.W["wl.fp.ln.b"], out_bf16=ws["h512"], rows=M)
+                ops.layernorm(ws["cf"], self.W["wl.fp.ln.g"], self.W["wl.fp.ln.b"], out_f16=ws["h512"], rows=M)
             else:
                 ops.gemm(src, self.W[f"wl.c{i}.w"], dst, act=ops.ACT_GELU, **common)
             src, dst = dst, src
@@ -348,7 +348,7 @@ class Engine:
         x = ws["x"]
         self._linear(ws["h512"], "wl.fp", x, M, 512, out_mode=ops.OUT_STORE_F32)
         # positional conv (k128, pad 64, 16 groups, weight-norm folded) + GELU, added to x: one implicit GEMM per group
-        ops.split_bf16(x, ws["hl"])
+        ops.split_f16(x, ws["hl"])
         G, K = c["pos_groups"], c["pos_k"]
         cg = d // G
         x3 = x.view(B, T, d)
@@ -361,11 +361,11 @@ class Engine:
         hd = d // H
         tab = self._rel_bias_table(T)
         if not large:
-            self._ln(x, "wl.enc.ln", out_f32=x, out_bf16=ws["h"])
+            self._ln(x, "wl.enc.ln", out_f32=x, out_f16=ws["h"])
         for i in range(a["layers"]):
             q = f"wl{i}."
             if large:
-                self._ln(x, q + "ln1", out_bf16=ws["h"])
+                self._ln(x, q + "ln1", out_f16=ws["h"])
             self._linear(ws["h"], q + "qkv", ws["qkv"], M, d)
             ops.wavlm_gate(ws["h"], d, B, T, H, hd, self.W[q + "gate.w"], self.W[q + "gate.b"], self.W[q + "gate.c"],
                            ws["gate"])
@@ -373,13 +373,13 @@ class Engine:
                           q_col=0, k_col=d, v_col=2 * d, rel_bias=tab, gate=ws["gate"])
             self._linear(ws["ctx"], q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
             if large:
-                self._ln(x, q + "ln2", out_bf16=ws["h"])
+                self._ln(x, q + "ln2", out_f16=ws["h"])
             else:
-                self._ln(x, q + "ln1", out_f32=x, out_bf16=ws["h"])
+                self._ln(x, q + "ln1", out_f32=x, out_f16=ws["h"])
             self._linear(ws["h"], q + "fc1", ws["u"], M, d, act=ops.ACT_GELU)
             self._linear(ws["u"], q + "fc2", x, M, a["ffn"], out_mode=ops.OUT_ADD_F32)
             if not large:
-                self._ln(x, q + "ln2", out_f32=x, out_bf16=ws["h"])
+                self._ln(x, q + "ln2", out_f32=x, out_f16=ws["h"])
         return ws, T
 
     # ------------------------------------------------------------------------------------ conformer
@@ -389,11 +389,11 @@ class Engine:
         x = ws["x"]
         Fd = self.ffx * d
         # x += 0.5 * FF1(x)
-        self._ln(x, q + "ff1.ln", out_bf16=ws["h"])
+        self._ln(x, q + "ff1.ln", out_f16=ws["h"])
         self._linear(ws["h"], q + "ff1.l1", ws["u"], M, d, act=ops.ACT_GELU)
         self._linear(ws["u"], q + "ff1.l2", x, M, Fd, out_mode=ops.OUT_ADD_F32, alpha=0.5)
         # x = ln1(x + MHA(x, x, x)); h = ln2(x)
-        ops.split_bf16(x, ws["hl"])
+        ops.split_f16(x, ws["hl"])
         hi = ws["hl"]
         w = self.W[q + "attn.in.w"]
         ops.gemm(hi, w, ws["qkv"], n=3 * d, slab_k=d, a_rows=M, a_cols=d, a_row_stride=2 * d, m_rows=M,
@@ -403,14 +403,14 @@ class Engine:
         ops.attention(ws["qkv"].view(B, T, 3 * d), ws["ctx"].view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5,
                       q_col=0, k_col=d, v_col=2 * d)
         self._linear(ws["ctx"], q + "attn.out", x, M, d, out_mode=ops.OUT_ADD_F32)
-        ops.layernorm(x, self.W[q + "ln1.g"], self.W[q + "ln1.b"], out_f32=x, out_bf16=ws["h"],
+        ops.layernorm(x, self.W[q + "ln1.g"], self.W[q + "ln1.b"], out_f32=x, out_f16=ws["h"],
                       gamma2=self.W[q + "ln2.g"], beta2=self.W[q + "ln2.b"])
         # conv module: pw1 -> GLU -> conv-k (BatchNorm folded) -> GELU -> pw2;  x += conv
-        self._linear(ws["h"], q + "pw1", ws["g"], M, d, out_mode=ops.OUT_GLU_BF16, tile_n=256)
+        self._linear(ws["h"], q + "pw1", ws["g"], M, d, out_mode=ops.OUT_GLU_F16, tile_n=256)
         self._conv(ws["g"], q + "conv", ws["c"], B, T, d, self.conf_k, 1, act=ops.ACT_GELU)
         self._linear(ws["c"], q + "pw2", x, M, d, out_mode=ops.OUT_ADD_F32)
         # x += 0.5 * FF2(x)
-        self._ln(x, q + "ff2.ln", out_bf16=ws["h"])
+        self._ln(x, q + "ff2.ln", out_f16=ws["h"])
         self._linear(ws["h"], q + "ff2.l1", ws["u"], M, d, act=ops.ACT_GELU)
         self._linear(ws["u"], q + "ff2.l2", x, M, Fd, out_mode=ops.OUT_ADD_F32, alpha=0.5)
 
@@ -429,7 +429,7 @@ class Engine:
             final_ln = "enc.ln"
         else:
             ws, T = self._wavlm_encoder(wave, B)
-            # wavlm-large ends with encoder.layer_norm; wavlm-base(-plus) is post-LN: x is final and ws["h"] = bf16(x)
+            # wavlm-large ends with encoder.layer_norm; wavlm-base(-plus) is post-LN: x is final and ws["h"] = f16(x)
             final_ln = "wl.enc.ln" if self.arch["stable_ln"] else None
         x = ws["x"]
         M = B * T
@@ -449,16 +449,16 @@ class Engine:
             ws = self._buffers(B, mll)
             ws["x"].copy_(xs)
             x, T, M = ws["x"], mll, B * mll
-            ops.split_bf16(x, ws["hl"])
+            ops.split_f16(x, ws["hl"])
             if lang_id is not None:
                 self._lang_proj(ws["hl"], 2 * d, lang_id, ws, B, T, bilstm)
             elif bilstm:
                 ws["h"].view(B, T, d).copy_(ws["hl"].view(B, T, 2 * d)[:, :, :d])
         elif lang_id is not None:
-            self._ln(x, final_ln, out_bf16=ws["h"])
+            self._ln(x, final_ln, out_f16=ws["h"])
             self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
         elif bilstm:
-            self._ln(x, final_ln, out_bf16=ws["h"])
+            self._ln(x, final_ln, out_f16=ws["h"])
         else:
             self._ln(x, final_ln, out_f32=x)
         if bilstm:
@@ -469,23 +469,23 @@ class Engine:
                 last = layer == self.lstm_layers - 1
                 self._linear(a_in, f"lstm{layer}.in", ws["gx"], M, d, out_mode=ops.OUT_STORE_F32)
                 ops.lstm_layer(ws["gx"], self.W[f"lstm{layer}.whh"], B, T, Hs,
-                               y_bf16=None if last else ws["ctx"], y_f32=x if last else None)
+                               y_f16=None if last else ws["ctx"], y_f32=x if last else None)
                 a_in = ws["ctx"]
         for i in range(self.n_conf):
             self._conformer(i, ws, B, T)
         # tail: dilated stack -> classifier (split precision) + boundary-offset head
         src = x
         if self.dil_depth > 0:
-            ops.split_bf16(x, ws["hl"])
+            ops.split_f16(x, ws["hl"])
             a_in, ars = ws["hl"], 2 * d
             for i in range(self.dil_depth):
                 last = i == self.dil_depth - 1
                 out = ws["y"] if last else (ws["c"] if i % 2 == 0 else ws["g"])
                 self._conv(a_in, f"dil{i}", out, B, T, d, self.dil_k, 2 ** i, a_row_stride=ars, act=ops.ACT_RELU,
-                           out_mode=ops.OUT_STORE_F32 if last else ops.OUT_STORE_BF16)
+                           out_mode=ops.OUT_STORE_F32 if last else ops.OUT_STORE_F16)
                 a_in, ars = out, d
             src = ws["y"]
-        ops.split_bf16(src, ws["hl"])
+        ops.split_f16(src, ws["hl"])
         ops.gemm(ws["hl"], self.W["cls.w"], ws["logits"], n=self.Lp, slab_k=d, shifts=[0, 0, 0], cols=[0, d, 0],
                  a_rows=M, a_cols=2 * d, a_row_stride=2 * d, m_rows=M, out_row_stride=self.Lp, bias=self.W["cls.b"],
                  out_mode=ops.OUT_STORE_F32, tile_n=128)
@@ -493,15 +493,15 @@ class Engine:
         ops.rowdot_sigmoid(ws["c"], self.W["off.w"], self.W["off.b"], ws["offsets"])
         return ws["logits"][:, :, :self.L], ws["offsets"]
 
-    def _lang_proj(self, a, a_row_stride, lang_id, ws, B, T, to_bf16=False):
+    def _lang_proj(self, a, a_row_stride, lang_id, ws, B, T, to_f16=False):
         """REF/model.py:176-180 folded: x = W_h h + (W_e emb[lang] + b), one bias row per batch item.  The result feeds
-        the BiLSTM input GEMM (bf16, ws["h"]) or becomes the fp32 residual stream (ws["x"])."""
+        the BiLSTM input GEMM (f16, ws["h"]) or becomes the fp32 residual stream (ws["x"])."""
         d = self.d
         lang_id = lang_id.to(self.dev).long().view(-1)
         if lang_id.numel() != B:
             raise ValueError("lang_id must have one entry per batch item")
         bias = self.W["lang.bias"].index_select(0, lang_id).contiguous()  # [B, d]
-        ops.gemm(a, self.W["lang.w"], ws["h"] if to_bf16 else ws["x"], n=d, slab_k=d, a_rows=T, a_cols=d,
+        ops.gemm(a, self.W["lang.w"], ws["h"] if to_f16 else ws["x"], n=d, slab_k=d, a_rows=T, a_cols=d,
                  a_row_stride=a_row_stride, a_batch_stride=T * a_row_stride, batches=B, m_rows=T, out_row_stride=d,
                  out_batch_stride=T * d, bias=bias, bias_batch_stride=d,
-                 out_mode=ops.OUT_STORE_BF16 if to_bf16 else ops.OUT_STORE_F32)
+                 out_mode=ops.OUT_STORE_F16 if to_f16 else ops.OUT_STORE_F32)

@@ -42,12 +42,12 @@ def mel_filters(n_mels, sr=16000, fmin=0.0, fmax=8000.0):
 
 
 def dft_basis_split():
-    """bf16 [448][3*448] = [W_hi | W_mid | W_hi]: the DFT basis transposed (row = output column, K = sample index,
+    """f16 [448][3*448] = [W_hi | W_mid | W_hi]: the DFT basis transposed (row = output column, K = sample index,
     zero padded 400 -> 448) and split hi + mid for the split-precision tensor-core contraction in csrc/logmel.cu."""
     wt = torch.zeros(BASIS_COLS, BASIS_COLS)
     wt[:, :N_FFT] = torch.from_numpy(dft_basis()).t()
-    hi = wt.to(torch.bfloat16)
-    mid = (wt - hi.float()).to(torch.bfloat16)
+    hi = wt.to(torch.float16)
+    mid = (wt - hi.float()).to(torch.float16)
     return torch.cat([hi, mid, hi], dim=1).contiguous()
 
 

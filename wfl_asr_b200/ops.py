@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, MERGE_MODES, OUT_ADD_F32, OUT_GLU_BF16, OUT_STORE_BF16,  # noqa: F401
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, MERGE_MODES, OUT_ADD_F32, OUT_GLU_F16, OUT_STORE_F16,  # noqa: F401
                    OUT_STORE_F32, GemmDesc, Segment, WflError)
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -34,7 +34,7 @@ def _ptr(t):
 
 def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_stride, a_batch_stride=0, batches=1,
          m_rows=None, out_row_stride=None, out_batch_stride=0, bias=None, bias_batch_stride=0, act=ACT_NONE,
-         out_mode=OUT_STORE_BF16, alpha=1.0, tile_n=0):
+         out_mode=OUT_STORE_F16, alpha=1.0, tile_n=0):
     """acc[b,t,n] = sum_s sum_k A[b, t+shift_s, col_s+k] * W[n, s*slab_k+k]; see wfl_gemm in the header."""
     d = GemmDesc()
     d.a = a.data_ptr()
@@ -49,7 +49,7 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
     d.act, d.out_mode, d.alpha = act, out_mode, alpha
     d.out = out.data_ptr()
     d.m_rows = a_rows if m_rows is None else m_rows
-    out_cols = n // 2 if out_mode == OUT_GLU_BF16 else n
+    out_cols = n // 2 if out_mode == OUT_GLU_F16 else n
     d.out_row_stride = out_cols if out_row_stride is None else out_row_stride
     d.out_batch_stride = out_batch_stride
     d.tile_n = tile_n
@@ -68,47 +68,47 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
 
 
 def linear(a2d, w, out2d, **kw):
-    """a2d [M, K] bf16 (contiguous rows), w [N, K] bf16 -> out2d [M, N or N/2]."""
+    """a2d [M, K] f16 (contiguous rows), w [N, K] f16 -> out2d [M, N or N/2]."""
     M, K = a2d.shape
     gemm(a2d, w, out2d, n=w.shape[0], slab_k=K, a_rows=M, a_cols=K, a_row_stride=a2d.stride(0), m_rows=M,
          out_row_stride=out2d.stride(0), **kw)
 
 
 def attention(qkv, out, *, B, T, H, hd, scale, q_col, k_col, v_col, rel_bias=None, gate=None):
-    """qkv bf16 [B, T, W]; out bf16 [B, T, H*hd]."""
+    """qkv f16 [B, T, W]; out f16 [B, T, H*hd]."""
     rc = _lib.load().wfl_attention(_ptr(qkv), qkv.stride(1), qkv.stride(0), q_col, k_col, v_col, B, T, H, hd, scale,
                                    _ptr(rel_bias), _ptr(gate), _ptr(out), out.stride(1), out.stride(0), _stream())
     _lib.check(rc, "wfl_attention")
     _count()
 
 
-def layernorm(x, gamma, beta, *, out_f32=None, out_bf16=None, gamma2=None, beta2=None, eps=1e-5, act_bf16=ACT_NONE,
+def layernorm(x, gamma, beta, *, out_f32=None, out_f16=None, gamma2=None, beta2=None, eps=1e-5, act_f16=ACT_NONE,
               rows=None):
     rows = x.numel() // x.shape[-1] if rows is None else rows
     rc = _lib.load().wfl_layernorm(_ptr(x), rows, x.shape[-1], _ptr(gamma), _ptr(beta), _ptr(gamma2), _ptr(beta2), eps,
-                                   _ptr(out_f32), _ptr(out_bf16), act_bf16, _stream())
+                                   _ptr(out_f32), _ptr(out_f16), act_f16, _stream())
     _lib.check(rc, "wfl_layernorm")
     _count()
 
 
 def wavlm_conv0(wave, n_samples, w, gamma, beta, norm_mode, out, out_batch_stride, scratch):
-    """wave fp32 [B, >=n_samples] -> out bf16 [B, out_batch_stride/512 rows, 512] (conv k10 s5 + norm + GELU)."""
+    """wave fp32 [B, >=n_samples] -> out f16 [B, out_batch_stride/512 rows, 512] (conv k10 s5 + norm + GELU)."""
     rc = _lib.load().wfl_wavlm_conv0(_ptr(wave), wave.stride(0), n_samples, wave.shape[0], _ptr(w), _ptr(gamma),
                                      _ptr(beta), norm_mode, _ptr(out), out_batch_stride, _ptr(scratch), _stream())
     _lib.check(rc, "wfl_wavlm_conv0")
     _count(2)
 
 
-def wavlm_gate(x_bf16, row_stride, B, T, H, hd, gw, gb, gconst, gate):
-    rc = _lib.load().wfl_wavlm_gate(_ptr(x_bf16), row_stride, B, T, H, hd, _ptr(gw), _ptr(gb), _ptr(gconst), _ptr(gate),
+def wavlm_gate(x_f16, row_stride, B, T, H, hd, gw, gb, gconst, gate):
+    rc = _lib.load().wfl_wavlm_gate(_ptr(x_f16), row_stride, B, T, H, hd, _ptr(gw), _ptr(gb), _ptr(gconst), _ptr(gate),
                                     _stream())
     _lib.check(rc, "wfl_wavlm_gate")
     _count()
 
 
-def split_bf16(x, out):
+def split_f16(x, out):
     rows = x.numel() // x.shape[-1]
-    _lib.check(_lib.load().wfl_split_bf16(_ptr(x), rows, x.shape[-1], _ptr(out), _stream()), "wfl_split_bf16")
+    _lib.check(_lib.load().wfl_split_f16(_ptr(x), rows, x.shape[-1], _ptr(out), _stream()), "wfl_split_f16")
     _count()
 
 
@@ -118,9 +118,9 @@ def broadcast_rows(src, dst, batches):
     _count()
 
 
-def rowdot_sigmoid(x_bf16, w, b, out):
-    rows = x_bf16.numel() // x_bf16.shape[-1]
-    rc = _lib.load().wfl_rowdot_sigmoid(_ptr(x_bf16), rows, x_bf16.shape[-1], _ptr(w), _ptr(b), w.shape[0], _ptr(out),
+def rowdot_sigmoid(x_f16, w, b, out):
+    rows = x_f16.numel() // x_f16.shape[-1]
+    rc = _lib.load().wfl_rowdot_sigmoid(_ptr(x_f16), rows, x_f16.shape[-1], _ptr(w), _ptr(b), w.shape[0], _ptr(out),
                                         _stream())
     _lib.check(rc, "wfl_rowdot_sigmoid")
     _count()
@@ -135,9 +135,9 @@ def peak_normalize(samples_f64, clip_begin, n_clips, out, scratch_max, out_f64=N
 
 
 def logmel_scratch(B, n_mels, device):
-    """Scratch buffers of wfl_whisper_logmel: (planes bf16, dft fp32 [B,3000,448], logspec fp32, clip max)."""
+    """Scratch buffers of wfl_whisper_logmel: (planes f16, dft fp32 [B,3000,448], logspec fp32, clip max)."""
     from .frontend import PLANE_SAMPLES
-    return (torch.empty(2 * PLANE_SAMPLES * B + 4096, dtype=torch.bfloat16, device=device),
+    return (torch.empty(2 * PLANE_SAMPLES * B + 4096, dtype=torch.float16, device=device),
             torch.empty(B, 3000, 448, device=device), torch.empty(B, 3000, n_mels, device=device),
             torch.empty(B, device=device))
 
@@ -189,8 +189,8 @@ def htk_times(segs, n, start_out, end_out):
     _count()
 
 
-def lstm_layer(gx, whh, B, T, H, y_bf16=None, y_f32=None):
-    """gx fp32 [B, T, 8H] (columns [dir][unit][gate]); whh bf16 [2, 4H, H] -> y [B, T, 2H]."""
-    rc = _lib.load().wfl_lstm_layer(_ptr(gx), _ptr(whh), B, T, H, _ptr(y_bf16), _ptr(y_f32), _stream())
+def lstm_layer(gx, whh, B, T, H, y_f16=None, y_f32=None):
+    """gx fp32 [B, T, 8H] (columns [dir][unit][gate]); whh f16 [2, 4H, H] -> y [B, T, 2H]."""
+    rc = _lib.load().wfl_lstm_layer(_ptr(gx), _ptr(whh), B, T, H, _ptr(y_f16), _ptr(y_f32), _stream())
     _lib.check(rc, "wfl_lstm_layer")
     _count()

@@ -1,4 +1,4 @@
-"""Weight packing: reference ``state_dict`` tensors (fp32, reference layouts) -> the bf16 layouts the
+"""Weight packing: reference ``state_dict`` tensors (fp32, reference layouts) -> the f16 layouts the
 sm_100a kernels consume.  Pure tensor reshuffles and folds, done once at load time:
 
 * Conv1d [out, in, k] -> [out][tap][in] so each tap is one K-slab of the implicit GEMM
@@ -6,13 +6,17 @@ sm_100a kernels consume.  Pure tensor reshuffles and folds, done once at load ti
 * GLU value/gate rows interleaved per output tile (REF/model.py:31-32)
 * lang_proj split into W_h and a per-language bias  W_e @ emb[l] + b  (REF/model.py:176-180)
 * q/k/v projections concatenated (Whisper k_proj has no bias -> zeros)
-* hi/lo bf16 split of precision-critical tail weights (classifier)
+* hi/lo f16 split of precision-critical tail weights (classifier)
 """
 import torch
 
 
-def bf16(t):
-    return t.detach().to(torch.bfloat16).contiguous()
+F16_MAX = 65504.0
+
+
+def f16(t):
+    """fp32 -> the library's 16-bit operand type (IEEE fp16), saturating like the kernels' own conversions."""
+    return t.detach().float().clamp(-F16_MAX, F16_MAX).to(torch.float16).contiguous()
 
 
 def conv_taps(weight):
@@ -38,7 +42,7 @@ def fold_batchnorm(conv_w, conv_b, gamma, beta, mean, var, eps=1e-5):
 
 def interleave_glu(weight2d, bias, tile_n):
     """Rows [0,d) are GLU values, [d,2d) gates.  Reorder so each block of tile_n rows holds tile_n/2 values
-    followed by their tile_n/2 gates -- the layout WFL_OUT_GLU_BF16 expects."""
+    followed by their tile_n/2 gates -- the layout WFL_OUT_GLU_F16 expects."""
     two_d = weight2d.shape[0]
     d = two_d // 2
     h = tile_n // 2
@@ -51,9 +55,9 @@ def interleave_glu(weight2d, bias, tile_n):
 
 
 def split_hi_lo(weight2d):
-    """fp32 [n, k] -> bf16 [n, 3k] = [hi | hi | lo]: pairs with A = [hi | lo] slabs (cols 0, k, 0)."""
-    hi = weight2d.to(torch.bfloat16)
-    lo = (weight2d - hi.float()).to(torch.bfloat16)
+    """fp32 [n, k] -> f16 [n, 3k] = [hi | hi | lo]: pairs with A = [hi | lo] slabs (cols 0, k, 0)."""
+    hi = f16(weight2d)
+    lo = f16(weight2d.float() - hi.float())
     return torch.cat([hi, hi, lo], dim=1).contiguous()
 
 
