@@ -60,8 +60,9 @@ for w in which:
         # gemmN_K[_mode]
         parts = w[4:].split("_"); N, K = int(parts[0]), int(parts[1]); mode = int(parts[2]) if len(parts) > 2 else 0
         tile = int(parts[3]) if len(parts) > 3 else 0
+        act = int(parts[4]) if len(parts) > 4 else (ops.ACT_GELU if mode == 0 else 0)
         a = torch.randn(B * T, K, generator=g).to(dev).half(); wt = (torch.randn(N, K, generator=g) * K ** -0.5).to(dev).half()
         o = torch.zeros(B * T, N, device=dev, dtype=torch.float32 if mode in (1, 2) else torch.float16)
         bias = torch.zeros(N, device=dev)
-        ms = t_ms(lambda: ops.linear(a, wt, o, bias=bias, out_mode=mode, act=ops.ACT_GELU if mode == 0 else 0, tile_n=tile))
+        ms = t_ms(lambda: ops.linear(a, wt, o, bias=bias, out_mode=mode, act=act, tile_n=tile))
         print(f"{w}: {ms:.4f} ms  {2.0 * B * T * N * K / ms / 1e9:.1f} TFLOP/s")
