@@ -79,6 +79,27 @@ def test_lang_none_skips_projection():
     assert rel <= 2e-3 and agree_safe == 1.0
 
 
+@pytest.mark.parametrize("name", [n for n in ("whisper_base_full", "wavlm_base_plus") if n in SUPPORTED])
+def test_language_mean_fast_path(name):
+    """REF/infer.py:265-276 (no --lang-id): mean over per-language forwards.  The fast path runs the encoder once and
+    must equal the per-language full forwards bit for bit, and the fp32 oracle's mean within the logit tolerance."""
+    cfg, labels, sd, wave, lang, model = _build(name)
+    ids = list(range(cfg["model"]["num_languages"]))
+    B = wave.shape[0]
+    lm, om = model.forward_language_mean(wave.to(DEV), ids)
+    per = []
+    for i in ids:
+        lg, of = model(wave.to(DEV), torch.full((B,), i, dtype=torch.long, device=DEV))
+        per.append((lg.clone(), of.clone()))
+    assert torch.equal(lm, torch.stack([p[0] for p in per]).mean(dim=0))
+    assert torch.equal(om, torch.stack([p[1] for p in per]).mean(dim=0))
+    refs = [to.forward(wave, sd, cfg, torch.full((B,), i, dtype=torch.long)) for i in ids]
+    ref_l = torch.stack([r[0] for r in refs]).mean(dim=0)
+    ref_o = torch.stack([r[1] for r in refs]).mean(dim=0)
+    rel, agree, agree_safe, off_err = _compare(name + "/lang-mean", lm.float().cpu(), om.float().cpu(), ref_l, ref_o)
+    assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
+
+
 def test_cpu_input_fails_loudly():
     cfg, labels, sd, wave, lang, model = _build("whisper_base_cfg2")
     with pytest.raises(RuntimeError):
@@ -139,6 +160,21 @@ def test_label_stream_matches_synchronous_label():
     want = [lab.label(b.to(DEV), lang2) for b in batches]
     got = list(lab.label_stream(iter(batches), lang2))
     assert got == want and sum(len(s) for batch in got for s in batch) > 0
+
+
+def test_graph_replay_matches_direct_launches():
+    """label_host replays the whole pass from a CUDA graph: same segments as direct launches, also when the input
+    values and the language ids change between replays of one captured graph."""
+    cfg, labels, sd, wave, lang, model = _build("whisper_base_full")
+    direct = Labeler(model, median_filter=3, merge_mode="right", confidence_threshold=0.2, use_graphs=False)
+    graphed = Labeler(model, median_filter=3, merge_mode="right", confidence_threshold=0.2, use_graphs=True)
+    batch0 = torch.cat([wave, wave.flip(1) * 0.8], 0).pin_memory()
+    batch1 = torch.cat([wave.flip(1) * 0.6, wave * 0.9], 0).pin_memory()
+    n = batch0.shape[0]
+    for batch, lg in ((batch0, [0, 1]), (batch1, [1, 0]), (batch0, [1, 1])):
+        lt = torch.tensor((lg * n)[:n], device=DEV)
+        assert graphed.label_host(batch, lt) == direct.label_host(batch, lt)
+    assert len(graphed._graphs) == 1 and not direct._graphs
 
 
 def _write_wav(path, x, sr=16000):

@@ -417,12 +417,36 @@ class Engine:
     # ------------------------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, wave, lang_id=None, max_label_len=None):
+        ws, B, T, final_ln = self._encode(wave)
+        return self._head(ws, B, T, final_ln, lang_id, max_label_len)
+
+    @torch.no_grad()
+    def forward_languages(self, wave, lang_ids):
+        """REF/infer.py:265-276 runs the whole model once per language and averages; the encoder does not depend on the
+        language (REF/model.py:176-180 conditions its OUTPUT), so it runs once here and only lang_proj .. heads are
+        replayed.  Returns [(logits, offsets)] per language (clones), each bit-identical to ``forward(wave, lang)``."""
+        ws, B, T, final_ln = self._encode(wave)
+        d = self.d
+        enc = ws.get("enc")
+        if enc is None:
+            enc = ws["enc"] = torch.empty(B * T, d, device=self.dev, dtype=torch.float16)
+        if final_ln is not None:
+            self._ln(ws["x"], final_ln, out_f16=enc)
+        else:
+            enc.copy_(ws["h"])  # wavlm-base(-plus): the last post-LN already left f16(x) in ws["h"]
+        outs = []
+        for lid in lang_ids:
+            lt = torch.full((B,), int(lid), dtype=torch.long, device=self.dev)
+            logits, offsets = self._head(ws, B, T, final_ln, lt, None, enc=enc)
+            outs.append((logits.clone(), offsets.clone()))
+        return outs
+
+    def _encode(self, wave):
         if not wave.is_cuda:
             raise RuntimeError("wfl_asr_b200 has no CPU path: input_values must be a CUDA tensor")
         if wave.dim() != 2:
             raise ValueError("input_values must be [batch, samples]")
         B = wave.shape[0]
-        d = self.d
         if self.arch["type"] == "whisper":
             ws = self._buffers(B, 1500)
             T = self._whisper_encoder(wave, ws, B)
@@ -431,12 +455,23 @@ class Engine:
             ws, T = self._wavlm_encoder(wave, B)
             # wavlm-large ends with encoder.layer_norm; wavlm-base(-plus) is post-LN: x is final and ws["h"] = f16(x)
             final_ln = "wl.enc.ln" if self.arch["stable_ln"] else None
+        return ws, B, T, final_ln
+
+    def _head(self, ws, B, T, final_ln, lang_id, max_label_len, enc=None):
+        """Everything after the encoder (REF/model.py:166-194).  ``enc``: f16 encoder output kept by
+        forward_languages (final LayerNorm already applied); otherwise it is produced here from ws["x"] / ws["h"]."""
+        d = self.d
         x = ws["x"]
         M = B * T
         bilstm = self.m.get("enable_bilstm", True)
-        if final_ln is None and max_label_len is None:
+        lstm_in = ws["h"]
+        if enc is not None:
+            self._lang_proj(enc, d, lang_id, ws, B, T, bilstm)
+            lstm_in = ws["g"]
+        elif final_ln is None and max_label_len is None:
             if lang_id is not None:
                 self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
+                lstm_in = ws["g"]
         elif max_label_len is not None:
             # REF/model.py:166-174 (training/eval only): fix T to the label length; rare path, torch glue
             if final_ln is not None:
@@ -452,18 +487,21 @@ class Engine:
             ops.split_f16(x, ws["hl"])
             if lang_id is not None:
                 self._lang_proj(ws["hl"], 2 * d, lang_id, ws, B, T, bilstm)
+                lstm_in = ws["g"]
             elif bilstm:
                 ws["h"].view(B, T, d).copy_(ws["hl"].view(B, T, 2 * d)[:, :, :d])
+                lstm_in = ws["h"]
         elif lang_id is not None:
             self._ln(x, final_ln, out_f16=ws["h"])
             self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
+            lstm_in = ws["g"]
         elif bilstm:
             self._ln(x, final_ln, out_f16=ws["h"])
         else:
             self._ln(x, final_ln, out_f32=x)
         if bilstm:
             # REF/model.py:182-183: input projection for all steps as one GEMM, then the serial recurrence
-            a_in = ws["h"]
+            a_in = lstm_in
             Hs = d // 2
             for layer in range(self.lstm_layers):
                 last = layer == self.lstm_layers - 1
@@ -495,13 +533,14 @@ class Engine:
 
     def _lang_proj(self, a, a_row_stride, lang_id, ws, B, T, to_f16=False):
         """REF/model.py:176-180 folded: x = W_h h + (W_e emb[lang] + b), one bias row per batch item.  The result feeds
-        the BiLSTM input GEMM (f16, ws["h"]) or becomes the fp32 residual stream (ws["x"])."""
+        the BiLSTM input GEMM (f16, ws["g"] -- never the buffer it reads: other CTAs still load those rows as their A
+        operand) or becomes the fp32 residual stream (ws["x"])."""
         d = self.d
         lang_id = lang_id.to(self.dev).long().view(-1)
         if lang_id.numel() != B:
             raise ValueError("lang_id must have one entry per batch item")
         bias = self.W["lang.bias"].index_select(0, lang_id).contiguous()  # [B, d]
-        ops.gemm(a, self.W["lang.w"], ws["h"] if to_f16 else ws["x"], n=d, slab_k=d, a_rows=T, a_cols=d,
+        ops.gemm(a, self.W["lang.w"], ws["g"] if to_f16 else ws["x"], n=d, slab_k=d, a_rows=T, a_cols=d,
                  a_row_stride=a_row_stride, a_batch_stride=T * a_row_stride, batches=B, m_rows=T, out_row_stride=d,
                  out_batch_stride=T * d, bias=bias, bias_batch_stride=d,
                  out_mode=ops.OUT_STORE_F16 if to_f16 else ops.OUT_STORE_F32)

@@ -202,15 +202,12 @@ def _forward_clips(sess, clips, lens, lang_id):
     logits_out, offsets_out = [None] * len(lens), [None] * len(lens)
     for ln, idx in groups.items():
         wave = clips[idx] if ln is None else clips[idx, :ln].contiguous()
-        acc_l = acc_o = None
-        for lid in lang_ids:  # REF/infer.py:265-276: mean over languages when --lang-id is unset
-            lt = torch.full((len(idx),), lid, dtype=torch.long, device=dev)
+        if len(lang_ids) == 1:
+            lt = torch.full((len(idx),), lang_ids[0], dtype=torch.long, device=dev)
             lg, of = model(wave, lt)
-            lg, of = lg.clone(), of.clone()
-            acc_l = lg if acc_l is None else acc_l + lg
-            acc_o = of if acc_o is None else acc_o + of
-        if len(lang_ids) > 1:
-            acc_l, acc_o = acc_l / len(lang_ids), acc_o / len(lang_ids)
+            acc_l, acc_o = lg.clone(), of.clone()
+        else:  # REF/infer.py:265-276: mean over languages when --lang-id is unset (encoder runs once here)
+            acc_l, acc_o = model.forward_language_mean(wave, lang_ids)
         for j, i in enumerate(idx):
             logits_out[i], offsets_out[i] = acc_l[j], acc_o[j]
     return logits_out, offsets_out

@@ -226,6 +226,21 @@ class BIOPhonemeTagger(nn.Module):
             raise RuntimeError("wfl_asr_b200.BIOPhonemeTagger is inference-only (eval mode); training is out of scope")
         return self.engine().forward(input_values, lang_id, max_label_len)
 
+    @torch.no_grad()
+    def forward_language_mean(self, input_values, lang_ids):
+        """Mean of ``forward(input_values, lang)`` over ``lang_ids`` -- what REF/infer.py:265-276 computes with one full
+        model pass per language when --lang-id is unset -- with the (language-independent) encoder run once."""
+        if self.training:
+            raise RuntimeError("wfl_asr_b200.BIOPhonemeTagger is inference-only (eval mode); training is out of scope")
+        lang_ids = [int(i) for i in lang_ids]
+        if not lang_ids:
+            raise ValueError("lang_ids is empty")
+        outs = self.engine().forward_languages(input_values, lang_ids)
+        # same accumulation order as the reference: torch.stack(...).mean(0) over languages in id order
+        logits = torch.stack([o[0] for o in outs]).mean(dim=0)
+        offsets = torch.stack([o[1] for o in outs]).mean(dim=0)
+        return logits, offsets
+
     def decode_predictions(self, logits):
         return torch.argmax(logits, dim=-1)  # REF/model.py:196-198
 

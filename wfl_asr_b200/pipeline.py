@@ -4,6 +4,8 @@ segments, with every per-frame result staying on the device (one D2H copy of the
 It is the batched equivalent of the per-file body of REF/infer.py:251-310 (single chunk) and
 REF/infer.py:98-184 (30 s chunks of long files: per-chunk decode, time shift, merge across chunks).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -34,8 +36,31 @@ def label_tables(labels):
     return phon, kind, ph
 
 
+class _GraphedPass:
+    """One labeling pass (forward + post-processing, ~120 kernel launches) over a FIXED input buffer, captured once
+    into a CUDA graph and replayed: the launches are issued by the driver from one cudaGraphLaunch instead of ~120
+    ctypes calls, which is what bounds the batch-1 latency (launch-bound) and keeps the host free to decode the
+    previous batch in label_stream.  Kernel arguments (pointers, tensor maps, thresholds) are baked in at capture."""
+
+    def __init__(self, labeler, wave, lang_id):
+        self.wave = wave
+        self.lang = None if lang_id is None else lang_id.clone()
+        labeler._pass(self.wave, self.lang)  # sizes the workspaces, sets kernel attributes, builds cached tables
+        torch.cuda.synchronize(wave.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = labeler._pass(self.wave, self.lang)
+
+    def replay(self, lang_id):
+        if self.lang is not None:
+            self.lang.copy_(lang_id, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 class Labeler:
-    def __init__(self, model, median_filter=1, merge_mode="right", confidence_threshold=0.0, ph_names_out=None):
+    def __init__(self, model, median_filter=1, merge_mode="right", confidence_threshold=0.0, ph_names_out=None,
+                 use_graphs=None):
         """``ph_names_out``: optional list mapping phoneme index -> output name (the canonical_to_lang remap of
         REF/infer.py:303-307); equal output names merge as equal labels (REF/utils.py:148-186)."""
         if merge_mode not in ops.MERGE_MODES:
@@ -54,6 +79,11 @@ class Labeler:
         self.ph = torch.tensor(ph, dtype=torch.int32, device=self.dev)
         self.set_output_names(ph_names_out)
         self._ws = {}
+        # CUDA-graph replay of whole passes in the host-buffer entry points (label_host / label_stream)
+        self.use_graphs = (os.environ.get("WFL_NO_GRAPHS", "") == "") if use_graphs is None else bool(use_graphs)
+        self._graphs = {}
+        self._static_in = {}
+        self._stream_slots = [None, None]
 
     def set_output_names(self, names):
         self.out_names = list(names) if names is not None else list(self.phon)
@@ -103,6 +133,24 @@ class Labeler:
                            ws["merged"], ws["nout"])
         return ids, ws["merged"], ws["nout"], file_clip_begin, n_files
 
+    def _pass(self, wave, lang_id):
+        logits, offsets = self.model(wave, lang_id)
+        _, merged, nout, fcb, n_files = self.postprocess(logits, offsets)
+        return merged, nout, fcb, n_files, logits.shape[1]
+
+    def _run(self, wave, lang_id):
+        """One pass over a device buffer that will be reused by later calls: replayed from a CUDA graph when enabled."""
+        if not self.use_graphs:
+            return self._pass(wave, lang_id)
+        key = (wave.data_ptr(), tuple(wave.shape), lang_id is None, id(self.model.engine()), self.threshold, self.median,
+               self.merge_mode, None if self.ph_class is None else self.ph_class.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[key] = _GraphedPass(self, wave, lang_id)
+        return g.replay(lang_id)
+
     @torch.no_grad()
     def label(self, wave, lang_id=None, file_clip_begin=None, time_shift=None):
         """wave [B, N] fp32 on the device -> list (per file) of [(start, end, phoneme)] python tuples."""
@@ -113,8 +161,15 @@ class Labeler:
     @torch.no_grad()
     def label_host(self, wave_host, lang_id=None):
         """End-to-end call with HOST buffers: (pinned) fp32 [B, N] -> H2D -> label -> D2H -> python segments."""
-        wave = wave_host.to(self.dev, non_blocking=True)
-        return self.label(wave, lang_id)
+        shape = tuple(wave_host.shape)
+        wave = self._static_in.get(shape)
+        if wave is None:
+            if len(self._static_in) >= 4:
+                self._static_in.pop(next(iter(self._static_in)))
+            wave = self._static_in[shape] = torch.empty(shape, dtype=torch.float32, device=self.dev)
+        wave.copy_(wave_host, non_blocking=True)
+        merged, nout, fcb, n_files, T = self._run(wave, lang_id)
+        return self.fetch(merged, nout, fcb, n_files, T)
 
     @torch.no_grad()
     def label_stream(self, host_batches, lang_id=None):
@@ -126,7 +181,7 @@ class Labeler:
         main = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
         it = iter(host_batches)
-        slots = [None, None]  # device staging (double buffered)
+        slots = self._stream_slots  # device staging (double buffered); persistent so captured graphs stay valid
         ready = [torch.cuda.Event(), torch.cuda.Event()]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -153,9 +208,8 @@ class Labeler:
         while cur is not None:
             nxt = prefetch((i + 1) & 1)
             main.wait_event(ready[cur])
-            logits, offsets = self.model(slots[cur], lang_id)
+            merged, nout, fcb, n_files, T = self._run(slots[cur], lang_id)
             freed[cur].record(main)
-            _, merged, nout, fcb, n_files = self.postprocess(logits, offsets)
             k = i & 1
             if host_rec[k] is None or host_rec[k].shape != merged.shape:
                 host_rec[k] = torch.empty(merged.shape, dtype=torch.uint8).pin_memory()
@@ -166,7 +220,7 @@ class Labeler:
             done.record(main)
             if pending is not None:  # decode the previous batch on the host while this one runs on the GPU
                 yield self._decode_host(host_rec, host_cnt, *pending)
-            pending = (k, done, logits.shape[1], n_files)
+            pending = (k, done, T, n_files)
             cur = nxt
             i += 1
         if pending is not None:
