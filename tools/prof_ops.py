@@ -5,7 +5,7 @@ import torch
 from wfl_asr_b200 import ops
 from wfl_asr_b200.frontend import whisper_frontend_constants
 dev = torch.device("cuda:0")
-B, T, d = 32, 1500, 512
+B, T, d = int(os.environ.get("PROF_B", "32")), 1500, 512
 which = sys.argv[1:] or ["attn64"]
 reps = int(os.environ.get("REPS", "2"))
 g = torch.Generator().manual_seed(0)

@@ -20,21 +20,42 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         __half* __restrict__ out_f16, int act) {
   pdl_launch_dependents();  // the GEMM that consumes this output may run its prologue while these rows finish
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
   const int nvec = d >> 2;
+  const float inv_d = 1.0f / static_cast<float>(d);
+  // Grid-stride over rows, one warp per row, with the NEXT row's loads issued before this row's arithmetic: the
+  // kernel is a pure HBM stream (4d bytes in, 2d..6d out per row), so what matters is that every warp always has a
+  // row in flight -- one-shot blocks of 8 rows spent ~25 % of a 30 us kernel in block launch/drain.
+  const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * 8;
+  int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 nxt[kLnMaxVec];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nvec) nxt[i] = xr[idx];
+    }
+  }
+  for (; row < rows; row += warp_stride) {
   float4 v[kLnMaxVec];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
-      v[i] = xr[idx];
+      v[i] = nxt[i];
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  const float inv_d = 1.0f / static_cast<float>(d);
+  if (row + warp_stride < rows) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (row + warp_stride) * d);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nvec) nxt[i] = xr[idx];
+    }
+  }
   float mean = warp_sum(s) * inv_d;
   float q = 0.f;
 #pragma unroll
@@ -68,7 +89,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  if (out_f16 == nullptr) return;
+  if (out_f16 == nullptr) continue;
   if (gamma2 != nullptr) {
     mean = warp_sum(s) * inv_d;
     q = 0.f;
@@ -101,6 +122,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const int idx = lane + i * 32;
     if (idx < nvec) orow[idx] = make_uint2(pack_f16(v[i].x, v[i].y), pack_f16(v[i].z, v[i].w));
   }
+  }  // row loop
 }
 
 __global__ void __launch_bounds__(256) split_f16_kernel(const float4* __restrict__ x, int64_t rows, int d4,
@@ -224,18 +246,23 @@ extern "C" int wfl_layernorm(const float* x, int64_t rows, int32_t d, const floa
                 kLnMaxVecLimit * 128);
   WFL_CHECK_ARG((gamma2 == nullptr) == (beta2 == nullptr), "wfl_layernorm: gamma2/beta2 must come together");
   if (rows <= 0) return WFL_OK;
-  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  // grid-stride: exactly the resident blocks (one wave, no tail), every warp streaming rows with the next row prefetched
+  auto resident_grid = [&](const void* kern) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    return static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, static_cast<int64_t>(num_sms()) * per_sm));
+  };
   // registers scale with the per-lane vector count, so pick the smallest instantiation (occupancy = bytes in flight)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __half* ob = static_cast<__half*>(out_f16);
   if (d <= 512)
-    layernorm_kernel<4><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
+    layernorm_kernel<4><<<resident_grid(reinterpret_cast<const void*>(layernorm_kernel<4>)), 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   else if (d <= 768)
-    layernorm_kernel<6><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
+    layernorm_kernel<6><<<resident_grid(reinterpret_cast<const void*>(layernorm_kernel<6>)), 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   else if (d <= 1024)
-    layernorm_kernel<8><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
+    layernorm_kernel<8><<<resident_grid(reinterpret_cast<const void*>(layernorm_kernel<8>)), 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   else
-    layernorm_kernel<12><<<grid, 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
+    layernorm_kernel<12><<<resident_grid(reinterpret_cast<const void*>(layernorm_kernel<12>)), 256, 0, st>>>(x, rows, d, gamma, beta, gamma2, beta2, eps, out_f32, ob, act_f16);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }
