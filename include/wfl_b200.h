@@ -151,6 +151,15 @@ int wfl_lstm_layer(const float* gx, const void* whh_f16, int32_t B, int32_t T, i
 int wfl_peak_normalize(const double* in, const int64_t* clip_begin, int32_t n_clips, float* out,
                        int64_t out_stride, double* out_f64, double* scratch_max, void* stream);
 
+/* ---- ingest: sinc resampling to the model rate (REF/infer.py:217-220 -> torchaudio.functional.resample on the
+ * float64 waveform: TORCHAUDIO/functional/functional.py _get_sinc_resample_kernel + _apply_sinc_resample_kernel) ----
+ * out[f*new + p] = sum_{k < 2*width+orig} bank[k][p] * x[f*orig + k - width] (x = 0 outside [0, n_in)), fp64.
+ * orig/new_rate are the rates divided by their gcd; bank is the tap-major polyphase filter bank [2*width+orig][new_rate]
+ * built by the host (ingest.sinc_resample_bank); n_out = ceil(new_rate * n_in / orig) like the reference.
+ */
+int wfl_resample_sinc(const double* x, int64_t n_in, int32_t orig, int32_t new_rate, int32_t width,
+                      const double* bank, double* out, int64_t n_out, void* stream);
+
 /* ---- K1: Whisper log-mel front-end (TF/models/whisper/feature_extraction_whisper.py:135-164) --
  * wave fp32 [B][wave_stride] (n_samples valid, zero-extended/truncated to 480000).  The windowed DFT is a
  * tensor-core contraction over an overlapping-row view of the reflect-padded waveform in split precision

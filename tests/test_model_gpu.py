@@ -184,8 +184,8 @@ def _write_wav(path, x, sr=16000):
         f.write(b"data" + struct.pack("<I", len(pcm)) + pcm)
 
 
-@pytest.mark.parametrize("seconds", [4.0, 47.3])
-def test_infer_audio_end_to_end(tmp_path, seconds):
+@pytest.mark.parametrize("seconds,file_sr", [(4.0, 16000), (47.3, 16000), (5.0, 44100)])
+def test_infer_audio_end_to_end(tmp_path, seconds, file_sr):
     """infer.py entry point: config.yaml + phonemes.txt + langs.txt + checkpoint + wav -> .lab, against the oracle
     chain (peak normalise, <=30 s chunks, forward, threshold, median, decode, shift, merge, save_lab)."""
     from wfl_asr_b200 import infer
@@ -198,9 +198,9 @@ def test_infer_audio_end_to_end(tmp_path, seconds):
     with open(tmp_path / "config.yaml", "w") as f:
         yaml.safe_dump(cfg, f)
     torch.save(sd, tmp_path / "best_model.pt")
-    x = to.synth_wave(77, seconds) * 0.8
+    x = to.synth_wave(77, seconds, sr=file_sr) * 0.8
     wav = tmp_path / "clip.wav"
-    _write_wav(str(wav), x)
+    _write_wav(str(wav), x, sr=file_sr)
     out_lab = tmp_path / "out" / "clip.lab"
     segs = infer.infer_audio(str(wav), str(tmp_path / "config.yaml"), str(tmp_path / "best_model.pt"), str(out_lab),
                              device="cuda:0", lang_id=1, confidence_threshold=0.1)
@@ -208,6 +208,9 @@ def test_infer_audio_end_to_end(tmp_path, seconds):
     assert text == "".join(po.lab_lines(segs))
     # oracle chain on the same file
     audio, sr = infer.read_audio(str(wav))
+    if sr != 16000:  # REF/infer.py:217-220
+        from oracle import resample_oracle as ro
+        audio, sr = ro.resample(audio, sr, 16000), 16000
     audio = po.peak_normalize(audio)
     chunks = [audio] if len(audio) / sr <= 30.0 else [audio[s:s + 480000] for s in range(0, len(audio), 480000)]
     all_segs, t, n_frames, n_agree = [], 0.0, 0, 0

@@ -420,3 +420,18 @@ def test_lstm_layer(H, B, T):
     ops.lstm_layer(gx, whh, B, T, H, y_f16=y16, y_f32=y32)
     _report("lstm f32", y32, ref.to(DEV), 1.5e-2)  # h_{t-1} enters the recurrent product in f16
     _report("lstm f16", y16, ref.to(DEV), 2e-2)
+
+
+@pytest.mark.parametrize("sr,n", [(44100, 50000), (48000, 48001), (22050, 30011), (8000, 7999), (32000, 9), (44100, 1)])
+def test_resample_matches_oracle(sr, n):
+    """csrc/resample.cu (fp64 polyphase sinc bank) against the numpy restatement of torchaudio.functional.resample."""
+    from oracle import resample_oracle as ro
+    from wfl_asr_b200 import ingest
+    g = np.random.default_rng(sr + n)
+    x = g.standard_normal(n) * 0.3 + np.sin(np.arange(n) * 0.05)
+    want = ro.resample(x, sr, 16000)
+    got = ingest.resample(torch.from_numpy(x).to(DEV), sr, 16000).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-12
+    same = torch.from_numpy(x).to(DEV)
+    assert ingest.resample(same, 16000, 16000) is same

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import yaml
 
-from . import ops
+from . import ingest, ops
 from .model import BIOPhonemeTagger
 from .pipeline import FRAME_DURATION, Labeler
 from .utils import (canonical_to_lang, load_langs, load_phoneme_list, load_phoneme_merge_map, save_lab)
@@ -166,7 +166,7 @@ def _normalised_clips(audio, sr, dev):
     """REF/infer.py:234-244 + :113-115: whole-file peak normalisation, split into <= 30 s chunks when longer, each
     chunk normalised again by its own peak.  Returns (fp32 [n_clips, width] device tensor, chunk lengths)."""
     n = len(audio)
-    flat = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float64)).to(dev)
+    flat = audio if torch.is_tensor(audio) else torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float64)).to(dev)
     scratch = torch.empty(64, dtype=torch.float64, device=dev)
     if n / sr > MAX_SEGMENT_DURATION:
         step = int(MAX_SEGMENT_DURATION * sr)
@@ -236,13 +236,12 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
         print(f"Loaded forced phoneme list with {len(forced)} phonemes.")
 
     audio, sr = read_audio(audio_path)
-    target_sr = config["data"]["sample_rate"]
-    if sr != target_sr:
-        import torchaudio
-        audio = torchaudio.functional.resample(torch.tensor(audio), orig_freq=sr, new_freq=target_sr).numpy()
-        sr = target_sr
     if len(audio) == 0:
         raise ValueError(f"{audio_path}: empty audio")
+    target_sr = config["data"]["sample_rate"]
+    if sr != target_sr:  # REF/infer.py:217-220 (torchaudio.functional.resample on the host) -> csrc/resample.cu
+        audio = ingest.resample(ingest.to_device_mono(audio, dev), sr, target_sr)
+        sr = target_sr
 
     clips, lens, chunked = _normalised_clips(audio, sr, dev)
     if chunked:

@@ -134,6 +134,14 @@ def peak_normalize(samples_f64, clip_begin, n_clips, out, scratch_max, out_f64=N
     _count(2)
 
 
+def resample_sinc(x_f64, orig, new, width, bank, out_f64):
+    """x fp64 [n_in] (device) -> out fp64 [n_out]; orig/new already divided by their gcd; bank fp64 [2*width+orig, new]."""
+    rc = _lib.load().wfl_resample_sinc(_ptr(x_f64), x_f64.numel(), orig, new, width, _ptr(bank), _ptr(out_f64),
+                                       out_f64.numel(), _stream())
+    _lib.check(rc, "wfl_resample_sinc")
+    _count(1)
+
+
 def logmel_scratch(B, n_mels, device):
     """Scratch buffers of wfl_whisper_logmel: (planes f16, dft fp32 [B,3000,448], logspec fp32, clip max)."""
     from .frontend import PLANE_SAMPLES
