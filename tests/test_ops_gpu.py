@@ -48,6 +48,28 @@ def test_gemm_linear_f16(M, K, N, tile_n):
     _report("linear", out, ref, 1e-2)
 
 
+@pytest.mark.parametrize("M,N,tile_n", [(38528 + 77, 256, 256), (38528, 512, 256), (19200 + 640, 384, 128), (47999, 512, 0)])
+@pytest.mark.parametrize("mode", ["f16_gelu", "add_f32"])
+def test_gemm_large_pair(M, N, tile_n, mode):
+    """Problems with more tiles than SMs: CTA-pair kernel (cta_group::2, 256-row tiles), several persistent rounds,
+    ragged last M tile.  Run the file a second time with WFL_GEMM_PAIR=0 to put the single-CTA kernel through the
+    same shapes."""
+    K = 192
+    a = _rand(M, K, seed=41).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=42).half()
+    bias = _rand(N, seed=43)
+    pre = a.float() @ w.float().T + bias
+    if mode == "f16_gelu":
+        out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+        ops.linear(a, w, out, bias=bias, act=ops.ACT_GELU, tile_n=tile_n)
+        _report("large gelu", out, F.gelu(pre), 2e-3)
+    else:
+        resid = _rand(M, N, seed=44)
+        x = resid.clone()
+        ops.linear(a, w, x, bias=bias, out_mode=ops.OUT_ADD_F32, alpha=0.5, tile_n=tile_n)
+        _report("large add", x, resid + 0.5 * pre, 1e-5)
+
+
 @pytest.mark.parametrize("act", [ops.ACT_GELU, ops.ACT_RELU])
 def test_gemm_activations(act):
     M, K, N = 384, 256, 512
