@@ -4,7 +4,9 @@
 // layer l>0 consumes [fwd | bwd] of layer l-1).  The input projection x W_ih^T + b_ih + b_hh is one dense
 // GEMM (gemm.cu) for all time steps; this kernel runs the T strictly serial steps
 //     a_t = gx_t + W_hh h_{t-1};  c_t = s(f) c_{t-1} + s(i) tanh(g);  h_t = s(o) tanh(c_t)
-// One cluster of 8 CTAs owns one direction for a group of 8 batch items:
+// One cluster of 8 CTAs owns one direction for a group of NB = 8 or 16 batch items (16 = two n8 MMA column tiles
+// sharing the register-resident W_hh fragments; chosen when 8-item groups would need more clusters than the GPU
+// can keep resident at once, which would serialise the sequence twice):
 //   * W_hh (f16) never leaves the register file: CTA r holds the 4 gate rows of hidden units
 //     [r*H/8, (r+1)*H/8) as mma.sync m16n8k16 A-fragments, split over (unit group) x (K half) warps.
 //     Row tiles are arranged (i|f) and (g|o) per 8 units, so one thread ends up with all four gate
@@ -14,11 +16,12 @@
 //     meets at one barrier.cluster per step.  c_t stays in fp32 registers for the whole sequence.
 //   * gx_t is prefetched one step ahead as float4 (columns are packed [dir][unit][gate]).
 // The recurrence is latency-bound (T serial steps), not FLOP-bound: report steps/s, not a roofline fraction.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wfl {
 
-constexpr int kLstmNB = 8;  // batch items per cluster = one n8 MMA tile
 
 __device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -45,8 +48,9 @@ __device__ __forceinline__ float tanh_acc(float x) {
 
 // CL = CTAs per cluster: 8 (portable) up to H = 384; 16 (non-portable, opt-in) for H = 512 / 640 so that each CTA's
 // W_hh slice (4 * H/CL rows x H) still fits the register file as MMA fragments.
-template <int H, int CL>
+template <int H, int CL, int NB>
 struct LstmCfg {
+  static constexpr int kNT = NB / 8;                // n8 MMA column tiles (batch groups of 8)
   static constexpr int kUnits = H / CL;             // hidden units per CTA
   static constexpr int kGroups = kUnits / 8;        // 8-unit groups, one (pair of) warp(s) each
   static constexpr int kKSplit = 2;
@@ -54,23 +58,26 @@ struct LstmCfg {
   static constexpr int kThreads = kWarps * 32;
   static constexpr int kKTiles = H / 16 / kKSplit;  // k16 tiles per warp
   static constexpr int kHStride = H + 8;            // padded row (bank-conflict-free B fragments)
-  static constexpr int kHBufBytes = 2 * kLstmNB * kHStride * 2;
-  static constexpr int kStageBytes = kLstmNB * kUnits * 2;  // this CTA's h slice, [n][unit] f16
-  static constexpr int kPartBytes = kGroups * 32 * 8 * 4;   // K-half partial sums
+  static constexpr int kHBufBytes = 2 * NB * kHStride * 2;
+  static constexpr int kStageBytes = NB * kUnits * 2;  // this CTA's h slice, [n][unit] f16
+  static constexpr int kPartFloats = kGroups * 32 * 8 * kNT;  // K-half partial sums
   static constexpr int kVecPerRow = kUnits * 2 / 16;        // 16-byte vectors per (n) row of the slice
+  static_assert(NB == 8 || NB == 16, "8 or 16 batch items per cluster");
   static_assert(H % (CL * 8) == 0, "H must be a multiple of 8 * cluster size");
   static_assert((kUnits * 2) % 16 == 0, "slice rows must be 16-byte multiples");
 };
 
-template <int H, int CL>
-__global__ void __launch_bounds__((LstmCfg<H, CL>::kThreads), 1)
+template <int H, int CL, int NB>
+__global__ void __launch_bounds__((LstmCfg<H, CL, NB>::kThreads), 1)
 lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B, int T,
             __half* __restrict__ y_f16, float* __restrict__ y_f32) {
-  using Cfg = LstmCfg<H, CL>;
+  using Cfg = LstmCfg<H, CL, NB>;
   constexpr int kLstmCluster = CL;
+  constexpr int kLstmNB = NB;
+  constexpr int kNT = Cfg::kNT;
   __shared__ __align__(16) uint8_t hbuf_raw[Cfg::kHBufBytes];
   __shared__ __align__(16) uint8_t stage_raw[Cfg::kStageBytes];
-  __shared__ __align__(16) float part[Cfg::kGroups * 32 * 8];
+  __shared__ __align__(16) float part[Cfg::kPartFloats];
   __half* hbuf = reinterpret_cast<__half*>(hbuf_raw);  // [2][NB][kHStride]
   __half* stage = reinterpret_cast<__half*>(stage_raw);
 
@@ -110,77 +117,109 @@ lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B,
   for (int i = threadIdx.x; i < Cfg::kHBufBytes / 4; i += Cfg::kThreads) reinterpret_cast<uint32_t*>(hbuf_raw)[i] = 0u;
   cluster_sync_all();  // every CTA of the cluster is running and initialised before any DSMEM traffic
 
-  float c_state[2] = {0.f, 0.f};  // cells (unit, batch b0+2q), (unit, batch b0+2q+1); used by khalf==0 warps
-  const int bq0 = b0 + 2 * q, bq1 = b0 + 2 * q + 1;
+  // cells (unit, batch b0 + 8 nt + 2q) and (.. + 2q + 1) per column tile nt; used by khalf==0 warps
+  float c_state[kNT][2];
+  int bq[kNT][2];
+#pragma unroll
+  for (int nt = 0; nt < kNT; ++nt) {
+    c_state[nt][0] = c_state[nt][1] = 0.f;
+    bq[nt][0] = b0 + nt * 8 + 2 * q;
+    bq[nt][1] = bq[nt][0] + 1;
+  }
   const int64_t row_stride = static_cast<int64_t>(8) * H;  // gx row: [dir][unit][gate]
   const float4* gx_base = reinterpret_cast<const float4*>(gx) + (static_cast<int64_t>(dir) * H + unit);
   auto gx_ptr = [&](int b, int t) { return gx_base + (static_cast<int64_t>(b) * T + t) * (row_stride / 4); };
-  float4 pre0 = make_float4(0.f, 0.f, 0.f, 0.f), pre1 = pre0;
+  float4 pre[kNT][2];
+#pragma unroll
+  for (int nt = 0; nt < kNT; ++nt) pre[nt][0] = pre[nt][1] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (khalf == 0) {
     const int t_first = dir == 0 ? 0 : T - 1;
-    if (bq0 < B) pre0 = __ldg(gx_ptr(bq0, t_first));
-    if (bq1 < B) pre1 = __ldg(gx_ptr(bq1, t_first));
+#pragma unroll
+    for (int nt = 0; nt < kNT; ++nt) {
+      if (bq[nt][0] < B) pre[nt][0] = __ldg(gx_ptr(bq[nt][0], t_first));
+      if (bq[nt][1] < B) pre[nt][1] = __ldg(gx_ptr(bq[nt][1], t_first));
+    }
   }
   const uint32_t hbuf_local = smem_u32(hbuf_raw);
 
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? s : T - 1 - s;
     const int cur = s & 1, nxt = cur ^ 1;
-    // ---- W_hh h_{t-1} for this warp's 16 gate rows x 2 tiles x 8 batch columns over its K half
-    // four independent accumulator chains (even / odd k-tiles) halve the dependent-MMA latency chain
-    float acc_if[4] = {0.f, 0.f, 0.f, 0.f}, acc_go[4] = {0.f, 0.f, 0.f, 0.f};
-    float acc_if2[4] = {0.f, 0.f, 0.f, 0.f}, acc_go2[4] = {0.f, 0.f, 0.f, 0.f};
+    // ---- W_hh h_{t-1} for this warp's 16 gate rows x 2 tiles x NB batch columns over its K half.  Independent
+    // accumulator chains halve the dependent-MMA latency: even / odd k-tiles for NB = 8, the two column tiles for 16.
+    constexpr int kChains = kNT == 1 ? 2 : kNT;
+    float acc_if[kChains][4], acc_go[kChains][4];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc_if[c][i] = acc_go[c][i] = 0.f;
     const __half* hrow = hbuf + (cur * kLstmNB + g) * Cfg::kHStride + khalf * Cfg::kKTiles * 16 + 2 * q;
 #pragma unroll
     for (int kt = 0; kt < Cfg::kKTiles; ++kt) {
-      const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16);
-      const uint32_t hb1 = *reinterpret_cast<const uint32_t*>(hrow + kt * 16 + 8);
-      if (kt & 1) {
-        mma_f16_16816(acc_if2, wa[kt], hb0, hb1);
-        mma_f16_16816(acc_go2, wb[kt], hb0, hb1);
-      } else {
-        mma_f16_16816(acc_if, wa[kt], hb0, hb1);
-        mma_f16_16816(acc_go, wb[kt], hb0, hb1);
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(hrow + nt * 8 * Cfg::kHStride + kt * 16);
+        const uint32_t hb1 = *reinterpret_cast<const uint32_t*>(hrow + nt * 8 * Cfg::kHStride + kt * 16 + 8);
+        const int c = kNT == 1 ? (kt & 1) : nt;
+        mma_f16_16816(acc_if[c], wa[kt], hb0, hb1);
+        mma_f16_16816(acc_go[c], wb[kt], hb0, hb1);
       }
     }
+    if constexpr (kNT == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc_if[i] += acc_if2[i];
-      acc_go[i] += acc_go2[i];
+      for (int i = 0; i < 4; ++i) {
+        acc_if[0][i] += acc_if[1][i];
+        acc_go[0][i] += acc_go[1][i];
+      }
     }
     if (khalf == 1) {
-      float4* pp = reinterpret_cast<float4*>(part + (group * 32 + lane) * 8);
-      pp[0] = make_float4(acc_if[0], acc_if[1], acc_if[2], acc_if[3]);
-      pp[1] = make_float4(acc_go[0], acc_go[1], acc_go[2], acc_go[3]);
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        float4* pp = reinterpret_cast<float4*>(part + ((group * kNT + nt) * 32 + lane) * 8);
+        pp[0] = make_float4(acc_if[nt][0], acc_if[nt][1], acc_if[nt][2], acc_if[nt][3]);
+        pp[1] = make_float4(acc_go[nt][0], acc_go[nt][1], acc_go[nt][2], acc_go[nt][3]);
+      }
     }
     __syncthreads();
     if (khalf == 0) {
-      const float4* pp = reinterpret_cast<const float4*>(part + (group * 32 + lane) * 8);
-      const float4 p_if = pp[0], p_go = pp[1];
       // this step's input pre-activations were requested one step ago; take them, then immediately request the next
-      // step's.  (Nothing may read pre0/pre1 again before the next iteration: a register copy of the in-flight load at
+      // step's.  (Nothing may read pre[] again before the next iteration: a register copy of the in-flight load at
       // the end of this block stalled ~1100 cycles per step on the scoreboard -- per-phase clock64 trace, profiles/.)
-      const float4 in0 = pre0, in1 = pre1;
+      float4 in[kNT][2];
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        in[nt][0] = pre[nt][0];
+        in[nt][1] = pre[nt][1];
+      }
       if (s + 1 < T) {
         const int tn = dir == 0 ? s + 1 : T - 2 - s;
-        if (bq0 < B) pre0 = __ldg(gx_ptr(bq0, tn));
-        if (bq1 < B) pre1 = __ldg(gx_ptr(bq1, tn));
+#pragma unroll
+        for (int nt = 0; nt < kNT; ++nt) {
+          if (bq[nt][0] < B) pre[nt][0] = __ldg(gx_ptr(bq[nt][0], tn));
+          if (bq[nt][1] < B) pre[nt][1] = __ldg(gx_ptr(bq[nt][1], tn));
+        }
       }
-      // accumulator layout: [0],[1] = first gate of the tile (rows g) for batch 2q, 2q+1; [2],[3] = second gate (rows g+8)
-      const float ai0 = acc_if[0] + p_if.x + in0.x, ai1 = acc_if[1] + p_if.y + in1.x;
-      const float af0 = acc_if[2] + p_if.z + in0.y, af1 = acc_if[3] + p_if.w + in1.y;
-      const float ag0 = acc_go[0] + p_go.x + in0.z, ag1 = acc_go[1] + p_go.y + in1.z;
-      const float ao0 = acc_go[2] + p_go.z + in0.w, ao1 = acc_go[3] + p_go.w + in1.w;
-      c_state[0] = sigmoid_acc(af0) * c_state[0] + sigmoid_acc(ai0) * tanh_acc(ag0);
-      c_state[1] = sigmoid_acc(af1) * c_state[1] + sigmoid_acc(ai1) * tanh_acc(ag1);
-      const float h0 = sigmoid_acc(ao0) * tanh_acc(c_state[0]);
-      const float h1 = sigmoid_acc(ao1) * tanh_acc(c_state[1]);
       const int ul = group * 8 + g;  // unit inside this CTA's slice
-      stage[(2 * q) * Cfg::kUnits + ul] = to_f16(h0);
-      stage[(2 * q + 1) * Cfg::kUnits + ul] = to_f16(h1);
-      if (y_f32 != nullptr) {
-        if (bq0 < B) y_f32[(static_cast<int64_t>(bq0) * T + t) * (2 * H) + dir * H + unit] = h0;
-        if (bq1 < B) y_f32[(static_cast<int64_t>(bq1) * T + t) * (2 * H) + dir * H + unit] = h1;
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        const float4* pp = reinterpret_cast<const float4*>(part + ((group * kNT + nt) * 32 + lane) * 8);
+        const float4 p_if = pp[0], p_go = pp[1];
+        const float4 in0 = in[nt][0], in1 = in[nt][1];
+        // accumulator layout: [0],[1] = first gate of the tile (rows g) for batch 2q, 2q+1; [2],[3] = second gate (rows g+8)
+        const float ai0 = acc_if[nt][0] + p_if.x + in0.x, ai1 = acc_if[nt][1] + p_if.y + in1.x;
+        const float af0 = acc_if[nt][2] + p_if.z + in0.y, af1 = acc_if[nt][3] + p_if.w + in1.y;
+        const float ag0 = acc_go[nt][0] + p_go.x + in0.z, ag1 = acc_go[nt][1] + p_go.y + in1.z;
+        const float ao0 = acc_go[nt][2] + p_go.z + in0.w, ao1 = acc_go[nt][3] + p_go.w + in1.w;
+        c_state[nt][0] = sigmoid_acc(af0) * c_state[nt][0] + sigmoid_acc(ai0) * tanh_acc(ag0);
+        c_state[nt][1] = sigmoid_acc(af1) * c_state[nt][1] + sigmoid_acc(ai1) * tanh_acc(ag1);
+        const float h0 = sigmoid_acc(ao0) * tanh_acc(c_state[nt][0]);
+        const float h1 = sigmoid_acc(ao1) * tanh_acc(c_state[nt][1]);
+        stage[(nt * 8 + 2 * q) * Cfg::kUnits + ul] = to_f16(h0);
+        stage[(nt * 8 + 2 * q + 1) * Cfg::kUnits + ul] = to_f16(h1);
+        if (y_f32 != nullptr) {
+          if (bq[nt][0] < B) y_f32[(static_cast<int64_t>(bq[nt][0]) * T + t) * (2 * H) + dir * H + unit] = h0;
+          if (bq[nt][1] < B) y_f32[(static_cast<int64_t>(bq[nt][1]) * T + t) * (2 * H) + dir * H + unit] = h1;
+        }
       }
     }
     __syncthreads();
@@ -210,14 +249,15 @@ lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B,
   }
 }
 
-template <int H, int CL>
-static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_f16, float* y_f32, cudaStream_t stream) {
-  using Cfg = LstmCfg<H, CL>;
+template <int H, int CL, int NB>
+static int launch_lstm_nb(const float* gx, const void* whh, int B, int T, void* y_f16, float* y_f32, cudaStream_t stream) {
+  using Cfg = LstmCfg<H, CL, NB>;
   constexpr int kLstmCluster = CL;
+  constexpr int kLstmNB = NB;
   if (CL > 8) {
     static bool allowed = false;
     if (!allowed) {
-      WFL_CUDA(cudaFuncSetAttribute(lstm_kernel<H, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      WFL_CUDA(cudaFuncSetAttribute(lstm_kernel<H, CL, NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       allowed = true;
     }
   }
@@ -233,9 +273,47 @@ static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_f
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  WFL_CUDA(cudaLaunchKernelEx(&cfg, lstm_kernel<H, CL>, gx, static_cast<const __half*>(whh), B, T,
+  WFL_CUDA(cudaLaunchKernelEx(&cfg, lstm_kernel<H, CL, NB>, gx, static_cast<const __half*>(whh), B, T,
                               static_cast<__half*>(y_f16), y_f32));
   return WFL_OK;
+}
+
+// 8 batch items per cluster while every cluster of the launch can be resident at once (one wave: the sequence is
+// walked once); 16 when 8-item groups would need a second wave.  Resident capacity comes from
+// cudaOccupancyMaxActiveClusters (GPC boundaries make it less than SMs / cluster size: 16 clusters of 8 do not fit
+// on a 148-SM B200).  Measured, H 384, T 1500: NB 8 1.65 us/step in one wave, 3.29 in two; NB 16 2.72.
+template <int H, int CL>
+static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_f16, float* y_f32, cudaStream_t stream) {
+  static const int forced = [] {
+    const char* e = getenv("WFL_LSTM_NB");
+    return e ? atoi(e) : 0;
+  }();
+  static const int capacity = [] {
+    using Cfg = LstmCfg<H, CL, 8>;
+    if (CL > 8) cudaFuncSetAttribute(lstm_kernel<H, CL, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, 64, 2);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lstm_kernel<H, CL, 8>, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = (num_sms() / CL) * 3 / 4;
+    }
+    return n;
+  }();
+  const int clusters8 = 2 * ((B + 7) / 8);
+  const bool wide = forced ? forced == 16 : clusters8 > capacity;
+  if constexpr (CL == 8) {  // the 16-CTA clusters (H 512 / 640) have neither the registers nor the shared memory for it
+    if (wide) return launch_lstm_nb<H, CL, 16>(gx, whh, B, T, y_f16, y_f32, stream);
+  }
+  return launch_lstm_nb<H, CL, 8>(gx, whh, B, T, y_f16, y_f32, stream);
 }
 
 }  // namespace wfl
