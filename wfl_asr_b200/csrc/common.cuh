@@ -245,12 +245,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the barrier at this offset in CTA `rank` of the cluster
+// arrive on the barrier at this offset in CTA `rank` of the cluster.  RELAXED on purpose: what the arrival publishes
+// (tensor-memory reads that tcgen05.wait::ld already completed) needs no memory fence, and a .release.cluster arrive
+// compiles to MEMBAR.ALL.GPU + ERRBAR, which made the arriving lane wait for every global store the warp had in
+// flight -- 26 % of the GEMM epilogue's samples in ncu (profiles/README.md).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
 }
