@@ -236,6 +236,45 @@ def test_infer_audio_end_to_end(tmp_path, seconds, file_sr):
     assert n_agree / n_frames >= 0.995
 
 
+@pytest.mark.parametrize("name,bucket", [("wavlm_base_plus", 8000), ("wavlm_base_plus", 1), ("whisper_base_cfg2", 8000)])
+def test_bulk_label_corpus_ragged(name, bucket):
+    """bulk.label_corpus (BASELINE configs[3]: utterances of different lengths, length-bucketed): per bucket batch the
+    logits match the fp32 oracle on the same zero-padded batch (the reference's batched caller pads without masks,
+    REF/train.py:22-36), every utterance is decoded on its own frame count, and the segments equal the reference
+    post-processing of the GPU's own tags and offsets exactly.  bucket=1 -> exact-length groups (per-file semantics)."""
+    from wfl_asr_b200 import bulk, shard
+    cfg, labels, sd, _, _, model = _build(name)
+    secs = [0.61, 1.37, 0.62, 2.0, 1.36, 0.9, 1.37]
+    waves = [to.synth_wave(300 + i, s).astype(np.float32) for i, s in enumerate(secs)]
+    lens = [len(w) for w in waves]
+    langs = [i % 2 for i in range(len(waves))]
+    got = bulk.label_corpus(model, waves, langs, median_filter=3, merge_mode="right", confidence_threshold=0.1,
+                            max_clips=3, bucket_samples=bucket)
+    assert len(got) == len(waves)
+    etype = cfg["model"]["encoder_type"]
+    plan = shard.plan_shards(lens, 1, etype)[0]
+    bsz = 480000 if etype == "whisper" else bucket
+    seen = 0
+    for padded, group in shard.bucket_batches(plan, lens, 3, 32 * 480000, bsz):
+        host = torch.zeros(len(group), padded)
+        for j, i in enumerate(group):
+            host[j, :lens[i]] = torch.from_numpy(waves[i])
+        lt = torch.tensor([langs[i] for i in group])
+        g_l, g_o = model(host.to(DEV), lt.to(DEV))
+        g_l, g_o = g_l.float().cpu(), g_o.float().cpu()
+        ref_l, ref_o = to.forward(host, sd, cfg, lt)
+        rel, agree, agree_safe, off_err = _compare(f"{name}/bulk{padded}", g_l, g_o, ref_l, ref_o)
+        assert rel <= 2e-3 and agree_safe == 1.0
+        for j, i in enumerate(group):
+            n_fr = min(g_l.shape[1], shard.frames_for(lens[i], etype))
+            ids = po.suppress_low_confidence_ids(g_l[j, :n_fr].numpy(), labels.index("O"), 0.1)
+            ids = po.median_filter_ids(ids, 3)
+            want = po.merge_adjacent_segments(po.decode_bio_tags([labels[k] for k in ids], 0.02, g_o[j, :n_fr].numpy()), "right")
+            assert got[i] == want, f"utterance {i} ({lens[i]} samples) differs"
+            seen += 1
+    assert seen == len(waves)
+
+
 def test_full_size_cfg2_properties():
     """BASELINE configs[1] at full size (whisper-base, 6 encoder layers + 4 Conformer, batch 32 x 30 s): size-independent
     properties -- run-to-run determinism (bitwise), batch invariance (clip i inside the batch == clip i alone, bitwise),
