@@ -74,7 +74,13 @@ typedef struct wfl_gemm_desc {
   float alpha;
   void* out; /* f16 or f32, logical [batches][m_rows][out_cols] */
   int64_t m_rows, out_row_stride, out_batch_stride; /* elements */
-  int32_t tile_n;                                     /* 0 = auto, else 64/128/256 */
+  int32_t tile_n;                                     /* 0 = auto, else 128/256 */
+  /* grouped contraction (Conv1d(groups=G): WavLM positional conv, TF/models/wavlm/modeling_wavlm.py:48-105):
+   * groups = 0/1: plain.  Group g reads A columns slab_a_col[s] + g * a_col_group_stride, W rows [g*n, (g+1)*n)
+   * (w is [groups*n][num_slabs*slab_k]), bias[g*n ..], and writes output columns g * out_col_group_stride + [0, n).
+   * One launch covers all groups (tiles of all groups share the persistent grid). */
+  int32_t groups;
+  int64_t a_col_group_stride, out_col_group_stride; /* elements */
 } wfl_gemm_desc;
 
 int wfl_gemm(const wfl_gemm_desc* desc, void* stream);

@@ -34,6 +34,8 @@ class GemmDesc(_C.Structure):
         ("out", _C.c_void_p),
         ("m_rows", _C.c_int64), ("out_row_stride", _C.c_int64), ("out_batch_stride", _C.c_int64),
         ("tile_n", _C.c_int32),
+        ("groups", _C.c_int32),
+        ("a_col_group_stride", _C.c_int64), ("out_col_group_stride", _C.c_int64),
     ]
 
 

@@ -56,6 +56,9 @@ struct GemmParams {
   int slab_shift[WFL_MAX_SLABS];
   int slab_col[WFL_MAX_SLABS];
   int n, m_tiles_per_batch, n_tiles, total_tiles;
+  int m_tiles_all;  // m tiles of one group (= m_tiles_per_batch * batches); tile -> (group, m tile, n tile)
+  int a_col_group_stride;
+  long long out_group_bytes;
   const float* bias;
   long long bias_batch_stride;
   float alpha;
@@ -186,13 +189,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       uint32_t phase = 0;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+        const int gm_tile = tile / p.n_tiles;
+        const int group = gm_tile / p.m_tiles_all;
+        const int m_tile = gm_tile - group * p.m_tiles_all;
         const int b = m_tile / p.m_tiles_per_batch;
         const int t0 = (m_tile % p.m_tiles_per_batch) * kTileRows + static_cast<int>(rank) * BM;
-        const int n0 = n_tile * BN + static_cast<int>(rank) * Cfg::kWRows;  // PAIR: this CTA's half of the W tile
+        // W rows of this tile: group's block of n rows, n tile, (PAIR: this CTA's half of the W tile)
+        const int n0 = group * p.n + n_tile * BN + static_cast<int>(rank) * Cfg::kWRows;
         for (int s = 0; s < p.num_slabs; ++s) {
           const int shift = p.slab_shift[s];
-          const int col = p.slab_col[s];
+          const int col = p.slab_col[s] + group * p.a_col_group_stride;
           for (int kb = 0; kb < p.kblocks_per_slab; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
@@ -263,10 +269,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int col_begin = half * kColsPerWarp;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++local) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int gm_tile = tile / p.n_tiles;
+      const int group = gm_tile / p.m_tiles_all;
+      const int m_tile = gm_tile - group * p.m_tiles_all;
       const int b = m_tile / p.m_tiles_per_batch;
       const int t0 = (m_tile % p.m_tiles_per_batch) * kTileRows + static_cast<int>(rank) * BM;
-      const int n0 = n_tile * BN;
+      const int n0 = n_tile * BN;  // column inside the group
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       // bias tile -> smem (double-buffered by accumulator stage; written by epilogue warp 0 and 4's lanes), pre-combined
@@ -275,7 +283,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       if ((ew & 3) == 0) {
         for (int i = lane + half * (BN / 2); i < (half + 1) * (BN / 2); i += 32) {
           const int n = n0 + i;
-          float bv = (p.bias != nullptr && n < p.n) ? __ldg(p.bias + b * p.bias_batch_stride + n) : 0.0f;
+          float bv = (p.bias != nullptr && n < p.n) ? __ldg(p.bias + b * p.bias_batch_stride + group * p.n + n) : 0.0f;
           if constexpr (OUT_MODE == WFL_OUT_ADD_F32) bv *= p.alpha;
           if constexpr (kGlu) {
             if (i >= BN / 2) bv *= -kLog2e;
@@ -289,7 +297,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      uint8_t* gbox = p.out + b * p.out_batch_bytes + static_cast<long long>(t0 + quarter * 32) * p.out_row_bytes;
+      uint8_t* gbox = p.out + b * p.out_batch_bytes + static_cast<long long>(t0 + quarter * 32) * p.out_row_bytes +
+                      group * p.out_group_bytes;
       const int rows_valid = p.m_rows - (t0 + quarter * 32);
 
       // One 32-column chunk at a time: TMEM -> registers -> math -> staging box -> coalesced global accesses.  The
@@ -494,7 +503,13 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
     const char* e = getenv("WFL_GEMM_PAIR");
     return e ? atoi(e) : -1;
   }();
-  const long tiles128 = ((d->m_rows + BM - 1) / BM) * d->batches * ((d->n + bn - 1) / bn);
+  const int groups = d->groups > 1 ? d->groups : 1;
+  if (groups > 1) {
+    WFL_CHECK_ARG(d->out_mode != WFL_OUT_GLU_F16 && d->bias_batch_stride == 0, "wfl_gemm: groups cannot be combined with GLU / per-batch bias");
+    WFL_CHECK_ARG(d->a_col_group_stride % 8 == 0 && (d->out_col_group_stride * esz) % 16 == 0,
+                  "wfl_gemm: group strides must keep 16-byte alignment");
+  }
+  const long tiles128 = ((d->m_rows + BM - 1) / BM) * d->batches * ((d->n + bn - 1) / bn) * groups;
   const bool pair = bn == 256 && (pair_env < 0 ? tiles128 >= num_sms() : pair_env != 0);
   const int tile_rows = pair ? 2 * BM : BM;
 
@@ -509,7 +524,7 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)d->num_slabs * d->slab_k, (uint64_t)d->n};
+    uint64_t dims[2] = {(uint64_t)d->num_slabs * d->slab_k, (uint64_t)d->n * groups};
     uint64_t strides[1] = {(uint64_t)d->num_slabs * d->slab_k * 2};
     uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};
     int rc = make_tensor_map(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, d->w, dims, strides, box,
@@ -526,7 +541,10 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
   p.n = d->n;
   p.m_tiles_per_batch = (int)((d->m_rows + tile_rows - 1) / tile_rows);
   p.n_tiles = (d->n + bn - 1) / bn;
-  p.total_tiles = p.m_tiles_per_batch * d->batches * p.n_tiles;
+  p.m_tiles_all = p.m_tiles_per_batch * d->batches;
+  p.total_tiles = p.m_tiles_all * p.n_tiles * groups;
+  p.a_col_group_stride = (int)d->a_col_group_stride;
+  p.out_group_bytes = (long long)d->out_col_group_stride * esz;
   p.bias = d->bias;
   p.bias_batch_stride = d->bias_batch_stride;
   p.alpha = d->alpha;

@@ -139,12 +139,13 @@ class Engine:
         bias = sd[pc + "bias"].float()
         G, K = c["pos_groups"], c["pos_k"]
         cg = d // G
-        for gi in range(G):
-            wt = w[gi * cg:(gi + 1) * cg].permute(0, 2, 1)  # [cg out, 128 taps, cg in]
-            wp = wt.new_zeros(cg, K, 64)  # each tap is one 64-wide K slab; channels past cg belong to the next group -> 0
-            wp[:, :, :cg] = wt
-            self._put(f"wl.pos{gi}.w", wp.reshape(cg, K * 64), "f16")
-            self._put(f"wl.pos{gi}.b", bias[gi * cg:(gi + 1) * cg])
+        # one grouped contraction: W [G*cg out, 128 taps * 64]; each tap is one 64-wide K slab of group g's input
+        # channels (A columns g*cg ..), channels past cg belong to the next group -> zero weights
+        wt = w.permute(0, 2, 1)  # [d out (group-major), 128 taps, cg in]
+        wp = wt.new_zeros(d, K, 64)
+        wp[:, :, :cg] = wt
+        self._put("wl.pos.w", wp.reshape(d, K * 64), "f16")
+        self._put("wl.pos.b", bias)
         self._pack_ln("wl.enc.ln", sd, "encoder.encoder.layer_norm")
         for i in range(a["layers"]):
             p, q = f"encoder.encoder.layers.{i}.attention.", f"wl{i}."
@@ -347,16 +348,14 @@ class Engine:
         # feature projection -> fp32 hidden states
         x = ws["x"]
         self._linear(ws["h512"], "wl.fp", x, M, 512, out_mode=ops.OUT_STORE_F32)
-        # positional conv (k128, pad 64, 16 groups, weight-norm folded) + GELU, added to x: one implicit GEMM per group
+        # positional conv (k128, pad 64, 16 groups, weight-norm folded) + GELU, added to x: ONE grouped implicit GEMM
         ops.split_f16(x, ws["hl"])
         G, K = c["pos_groups"], c["pos_k"]
         cg = d // G
-        x3 = x.view(B, T, d)
-        for gi in range(G):
-            ops.gemm(ws["hl"], self.W[f"wl.pos{gi}.w"], x3[:, :, gi * cg:], n=cg, slab_k=64,
-                     shifts=[j - K // 2 for j in range(K)], cols=[gi * cg] * K, a_rows=T, a_cols=d, a_row_stride=2 * d,
-                     a_batch_stride=T * 2 * d, batches=B, m_rows=T, out_row_stride=d, out_batch_stride=T * d,
-                     bias=self.W[f"wl.pos{gi}.b"], act=ops.ACT_GELU, out_mode=ops.OUT_ADD_F32, tile_n=128)
+        ops.gemm(ws["hl"], self.W["wl.pos.w"], x, n=cg, slab_k=64, shifts=[j - K // 2 for j in range(K)], cols=[0] * K,
+                 a_rows=T, a_cols=d, a_row_stride=2 * d, a_batch_stride=T * 2 * d, batches=B, m_rows=T, out_row_stride=d,
+                 out_batch_stride=T * d, bias=self.W["wl.pos.b"], act=ops.ACT_GELU, out_mode=ops.OUT_ADD_F32, tile_n=128,
+                 groups=G, a_col_group_stride=cg, out_col_group_stride=cg)
         H = a["heads"]
         hd = d // H
         tab = self._rel_bias_table(T)

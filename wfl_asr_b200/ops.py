@@ -34,8 +34,9 @@ def _ptr(t):
 
 def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_stride, a_batch_stride=0, batches=1,
          m_rows=None, out_row_stride=None, out_batch_stride=0, bias=None, bias_batch_stride=0, act=ACT_NONE,
-         out_mode=OUT_STORE_F16, alpha=1.0, tile_n=0):
-    """acc[b,t,n] = sum_s sum_k A[b, t+shift_s, col_s+k] * W[n, s*slab_k+k]; see wfl_gemm in the header."""
+         out_mode=OUT_STORE_F16, alpha=1.0, tile_n=0, groups=1, a_col_group_stride=0, out_col_group_stride=0):
+    """acc[b,t,n] = sum_s sum_k A[b, t+shift_s, col_s+k] * W[n, s*slab_k+k]; see wfl_gemm in the header.
+    groups > 1: Conv1d(groups=G) in one launch (w [G*n, K], bias [G*n], column strides per group)."""
     d = GemmDesc()
     d.a = a.data_ptr()
     d.a_rows, d.a_cols, d.a_row_stride, d.a_batch_stride, d.batches = a_rows, a_cols, a_row_stride, a_batch_stride, batches
@@ -53,6 +54,7 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
     d.out_row_stride = out_cols if out_row_stride is None else out_row_stride
     d.out_batch_stride = out_batch_stride
     d.tile_n = tile_n
+    d.groups, d.a_col_group_stride, d.out_col_group_stride = groups, a_col_group_stride, out_col_group_stride
     if not (a.is_cuda and w.is_cuda and out.is_cuda):
         raise WflError("wfl_gemm needs CUDA tensors (no CPU fallback exists)")
     timed = TIMING is not None and len(shifts) >= TIMING_MIN_SLABS
@@ -62,8 +64,8 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
     _lib.check(_lib.load().wfl_gemm(ctypes.byref(d), _stream()), "wfl_gemm")
     if timed:
         e1.record()
-        tag = f"M{batches * d.m_rows}xN{n}xK{len(shifts) * slab_k}/slabs{len(shifts)}/mode{out_mode}"
-        TIMING.append((tag, 2.0 * batches * d.m_rows * n * len(shifts) * slab_k, e0, e1))
+        tag = f"M{batches * d.m_rows}xN{n}xK{len(shifts) * slab_k}/slabs{len(shifts)}/mode{out_mode}" + (f"/g{groups}" if groups > 1 else "")
+        TIMING.append((tag, 2.0 * groups * batches * d.m_rows * n * len(shifts) * slab_k, e0, e1))
     _count()
 
 
