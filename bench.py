@@ -297,6 +297,9 @@ def main():
         return 0
 
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's own banner ("NCCL version ...", printed to stdout when the
+        # environment sets NCCL_DEBUG=VERSION/INFO) out of it
+        os.environ["NCCL_DEBUG"] = os.environ.get("WFL_NCCL_DEBUG", "WARN")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     line = run_ours(args, rank, world, local_rank)
     if rank == 0:
