@@ -236,6 +236,42 @@ def test_infer_audio_end_to_end(tmp_path, seconds, file_sr):
     assert n_agree / n_frames >= 0.995
 
 
+@pytest.mark.parametrize("name", ["whisper_base_cfg2", "wavlm_base_plus"])
+def test_infer_folder_batched_equals_per_file(tmp_path, name, capsys):
+    """infer_folder labels the folder in shared batches; every .lab must equal what infer_audio writes for the same
+    file alone (long file -> 30 s chunks, 44.1 kHz file -> resampled, forced phoneme list -> aligned), for the
+    single-language and the language-mean path."""
+    from wfl_asr_b200 import infer
+    cfg, labels, sd, _, _ = mfg.case_inputs(name)
+    cfg["output"] = {"save_dir": str(tmp_path)}
+    cfg["postprocess"] = {"median_filter": 3, "merge_segments": "right", "confidence_threshold": 0.1}
+    (tmp_path / "phonemes.txt").write_text("\n".join(labels) + "\n")
+    (tmp_path / "langs.txt").write_text("en,0\nja,1\n")
+    with open(tmp_path / "config.yaml", "w") as f:
+        yaml.safe_dump(cfg, f)
+    torch.save(sd, tmp_path / "best_model.pt")
+    folder = tmp_path / "wavs"
+    folder.mkdir()
+    whisper = cfg["model"]["encoder_type"] == "whisper"
+    specs = [("a.wav", 3.1, 16000), ("b.wav", 33.0 if whisper else 2.2, 16000), ("c.wav", 2.2, 44100), ("d.wav", 3.1, 16000)]
+    for fn, secs, sr in specs:
+        _write_wav(str(folder / fn), to.synth_wave(hash(fn) % 97, secs, sr=sr) * 0.7, sr=sr)
+    (folder / "d.txt").write_text("p3 p7 p1\n")
+    args = (str(tmp_path / "config.yaml"), str(tmp_path / "best_model.pt"))
+    for lang in (1, None):
+        out_dir = tmp_path / f"out_{lang}"
+        got = infer.infer_folder(str(folder), *args, output_dir=str(out_dir), device="cuda:0", lang_id=lang,
+                                 confidence_threshold=0.1, files_per_pass=3)
+        assert set(got) == {s[0] for s in specs}
+        for fn, _, _ in specs:
+            single = tmp_path / f"single_{lang}_{fn}.lab"
+            segs = infer.infer_audio(str(folder / fn), *args, str(single), device="cuda:0", lang_id=lang,
+                                     confidence_threshold=0.1)
+            assert got[fn] == segs, f"{fn} (lang {lang}) differs between folder and single-file labeling"
+            assert (out_dir / fn.replace(".wav", ".lab")).read_text() == single.read_text()
+    capsys.readouterr()
+
+
 @pytest.mark.parametrize("name,bucket", [("wavlm_base_plus", 8000), ("wavlm_base_plus", 1), ("whisper_base_cfg2", 8000)])
 def test_bulk_label_corpus_ragged(name, bucket):
     """bulk.label_corpus (BASELINE configs[3]: utterances of different lengths, length-bucketed): per bucket batch the

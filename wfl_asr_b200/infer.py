@@ -184,10 +184,11 @@ def _normalised_clips(audio, sr, dev):
     return out, [n], False
 
 
-def _forward_clips(sess, clips, lens, lang_id):
-    """Runs the model over clips (rows of a padded fp32 tensor).  Whisper pads/truncates every clip to 30 s itself;
-    WavLM is length-sensitive (no attention mask in the reference), so its clips are run
-    at their exact lengths, grouping equal lengths into one batch."""
+def _forward_clips(sess, clip_rows, lens, lang_id, batch_clips=32):
+    """Runs the model over clips (``clip_rows[i]``: fp32 device row holding ``lens[i]`` valid samples).  Whisper
+    pads/truncates every clip to 30 s itself (zero padding, as its feature extractor does), so clips of any files
+    batch together; WavLM is length-sensitive (no attention mask in the reference), so its
+    clips run at their exact lengths, equal lengths sharing a batch.  Returns per-clip (logits [T, L], offsets [T, 2])."""
     model, dev = sess.model, sess.device
     lang_ids = [lang_id] if lang_id is not None else list(sess.lang2id.values())
     if lang_id is not None and lang_id > max(sess.lang2id.values()):
@@ -200,32 +201,30 @@ def _forward_clips(sess, clips, lens, lang_id):
         for i, ln in enumerate(lens):
             groups.setdefault(ln, []).append(i)
     logits_out, offsets_out = [None] * len(lens), [None] * len(lens)
-    for ln, idx in groups.items():
-        wave = clips[idx] if ln is None else clips[idx, :ln].contiguous()
-        if len(lang_ids) == 1:
-            lt = torch.full((len(idx),), lang_ids[0], dtype=torch.long, device=dev)
-            lg, of = model(wave, lt)
-            acc_l, acc_o = lg.clone(), of.clone()
-        else:  # REF/infer.py:265-276: mean over languages when --lang-id is unset (encoder runs once here)
-            acc_l, acc_o = model.forward_language_mean(wave, lang_ids)
-        for j, i in enumerate(idx):
-            logits_out[i], offsets_out[i] = acc_l[j], acc_o[j]
+    for ln, members in groups.items():
+        for s0 in range(0, len(members), batch_clips):
+            idx = members[s0:s0 + batch_clips]
+            if ln is None:
+                width = max(lens[i] for i in idx)
+                wave = torch.zeros(len(idx), width, device=dev)
+                for j, i in enumerate(idx):
+                    wave[j, :lens[i]] = clip_rows[i][:lens[i]]
+            else:
+                wave = torch.stack([clip_rows[i][:ln] for i in idx])
+            if len(lang_ids) == 1:
+                lt = torch.full((len(idx),), lang_ids[0], dtype=torch.long, device=dev)
+                lg, of = model(wave, lt)
+                acc_l, acc_o = lg.clone(), of.clone()
+            else:  # REF/infer.py:265-276: mean over languages when --lang-id is unset (encoder runs once here)
+                acc_l, acc_o = model.forward_language_mean(wave, lang_ids)
+            for j, i in enumerate(idx):
+                logits_out[i], offsets_out[i] = acc_l[j], acc_o[j]
     return logits_out, offsets_out
 
 
-def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_model.pt",
-                output_lab_path=None, device="cuda", lang_id=None,
-                sample=False, top_k=0, top_p=0.0, temperature=1.0,
-                confidence_threshold=0.0):
-    """REF/infer.py:186-328."""
-    sess = _Session.get(config_path, checkpoint_path, device)
-    config, dev = sess.config, sess.device
-    lang_name = None
-    if lang_id is not None:
-        for n, i in sess.lang2id.items():
-            if i == lang_id:
-                lang_name = n
-                break
+def _prepare_file(sess, audio_path):
+    """REF/infer.py:191-244 for one file: forced phoneme list, decode, resample, normalise, split into <= 30 s chunks."""
+    dev = sess.device
     forced = None
     phoneme_txt = audio_path.replace(".wav", ".txt")
     if os.path.exists(phoneme_txt):
@@ -234,19 +233,45 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
             for line in f:
                 forced.extend(line.strip().split())
         print(f"Loaded forced phoneme list with {len(forced)} phonemes.")
-
     audio, sr = read_audio(audio_path)
+    return _prepare_audio(sess, audio_path, audio, sr, forced)
+
+
+def _prepare_audio(sess, audio_path, audio, sr, forced):
+    dev = sess.device
     if len(audio) == 0:
         raise ValueError(f"{audio_path}: empty audio")
-    target_sr = config["data"]["sample_rate"]
+    target_sr = sess.config["data"]["sample_rate"]
     if sr != target_sr:  # REF/infer.py:217-220 (torchaudio.functional.resample on the host) -> csrc/resample.cu
         audio = ingest.resample(ingest.to_device_mono(audio, dev), sr, target_sr)
         sr = target_sr
-
     clips, lens, chunked = _normalised_clips(audio, sr, dev)
     if chunked:
         print(f"Audio is too long ({len(audio)/sr:.1f}s), splitting...")
-    logits, offsets = _forward_clips(sess, clips, lens, lang_id)
+    return dict(path=audio_path, clips=clips, lens=lens, chunked=chunked, forced=forced, sr=sr)
+
+
+def _label_files(sess, files, lang_id, confidence_threshold):
+    """Forward + post-processing for a list of prepared files in one go (REF/infer.py:246-319 per file): all clips of
+    all files share the model batches, one post-processing pass decodes every clip and merges the chunks of each
+    file, one D2H copy brings all segment records back.  Returns one segment list per file."""
+    dev = sess.device
+    lang_name = None
+    if lang_id is not None:
+        for n, i in sess.lang2id.items():
+            if i == lang_id:
+                lang_name = n
+                break
+    rows, lens, shifts, begins = [], [], [], [0]
+    for f in files:
+        t = 0.0
+        for j, ln in enumerate(f["lens"]):  # REF/infer.py:180-182: chunk j starts where the previous ones ended
+            rows.append(f["clips"][j])
+            lens.append(ln)
+            shifts.append(t)
+            t += ln / f["sr"]
+        begins.append(len(rows))
+    logits, offsets = _forward_clips(sess, rows, lens, lang_id)
 
     labeler = sess.labeler
     labeler.threshold = float(confidence_threshold)
@@ -254,7 +279,7 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
     if sess.merge_map and lang_name:  # REF/infer.py:303-307 remap before merging
         names = [canonical_to_lang(p, lang_name, sess.merge_map) for p in labeler.phon]
     labeler.set_output_names(names)
-    # every clip of one encoder call has the same T for Whisper; WavLM chunks may differ -> pad to the longest
+    # every clip has the same T for Whisper; WavLM clips differ -> pad to the longest, decode each on its own length
     T = max(l.shape[0] for l in logits)
     n = len(lens)
     lg = torch.zeros(n, T, logits[0].shape[-1], device=dev)
@@ -264,16 +289,16 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
         lg[i, :logits[i].shape[0]] = logits[i]
         of[i, :offsets[i].shape[0]] = offsets[i]
         tl.append(logits[i].shape[0])
-    shifts, t = [], 0.0
-    for ln in lens:  # REF/infer.py:180-182
-        shifts.append(t)
-        t += ln / sr
     _, merged, nout, fcb, n_files = labeler.postprocess(
         lg, of, torch.tensor(tl, dtype=torch.int32, device=dev),
-        torch.tensor([0, n], dtype=torch.int32, device=dev),
-        torch.tensor(shifts, dtype=torch.float64, device=dev) if chunked else None)
-    segments_pred = labeler.fetch(merged, nout, fcb, n_files, T)[0]
+        torch.tensor(begins, dtype=torch.int32, device=dev),
+        torch.tensor(shifts, dtype=torch.float64, device=dev))  # + 0.0 for single-chunk files: exact in fp64
+    return labeler.fetch(merged, nout, fcb, n_files, T)
 
+
+def _finish_file(f, segments_pred, output_lab_path):
+    """REF/infer.py:312-328: optional forced-phoneme alignment, .lab output."""
+    forced = f["forced"]
     if forced is not None:
         aligned = align_phoneme_list(segments_pred, forced)
         if "SP" not in forced and "AP" not in forced:
@@ -282,7 +307,6 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
             segments_pred = before + aligned + after
         else:
             segments_pred = aligned
-
     if output_lab_path:
         dir_path = os.path.dirname(output_lab_path)
         if dir_path:
@@ -292,23 +316,55 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
     return segments_pred
 
 
+def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_model.pt",
+                output_lab_path=None, device="cuda", lang_id=None,
+                sample=False, top_k=0, top_p=0.0, temperature=1.0,
+                confidence_threshold=0.0):
+    """REF/infer.py:186-328."""
+    sess = _Session.get(config_path, checkpoint_path, device)
+    f = _prepare_file(sess, audio_path)
+    segments_pred = _label_files(sess, [f], lang_id, confidence_threshold)[0]
+    return _finish_file(f, segments_pred, output_lab_path)
+
+
 def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_path: str = "best_model.pt",
                  output_dir: str = "outputs", device: str = "cuda", lang_id: int = None,
-                 sample=False, top_k=0, top_p=0.0, temperature=1.0, confidence_threshold=0.0):
-    """REF/infer.py:330-357."""
+                 sample=False, top_k=0, top_p=0.0, temperature=1.0, confidence_threshold=0.0,
+                 files_per_pass: int = 128, decode_workers: int = 8):
+    """REF/infer.py:330-357, same files, same .lab outputs and the same per-file printout, but the folder is labeled
+    ``files_per_pass`` files at a time: their audio is decoded on a thread pool, and all their clips share the model
+    batches and one post-processing pass (``_label_files``) instead of one batch-1 pass per file."""
     wav_files = [f for f in os.listdir(folder_path) if f.lower().endswith(".wav")]
     os.makedirs(output_dir, exist_ok=True)
-    for wav_file in wav_files:
-        full_audio_path = os.path.join(folder_path, wav_file)
-        output_lab_path = os.path.join(output_dir, wav_file.replace(".wav", ".lab"))
-        print(f"\nInferencing: {wav_file}")
-        segments = infer_audio(audio_path=str(full_audio_path), config_path=str(config_path),
-                               checkpoint_path=str(checkpoint_path), output_lab_path=str(output_lab_path),
-                               device=device, lang_id=lang_id, sample=sample, top_k=top_k, top_p=top_p,
-                               temperature=temperature, confidence_threshold=confidence_threshold)
-        print("Predicted segments:")
-        for start, end, ph in segments:
-            print(f"({round(start, 2)}, {round(end, 2)}, {ph})")
+    sess = _Session.get(config_path, checkpoint_path, device)
+    results = {}
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, decode_workers)) as pool:
+        for s0 in range(0, len(wav_files), max(1, files_per_pass)):
+            names = wav_files[s0:s0 + max(1, files_per_pass)]
+            paths = [str(os.path.join(folder_path, w)) for w in names]
+            decoded = list(pool.map(read_audio, paths))
+            files = []
+            for w, path, (audio, sr) in zip(names, paths, decoded):
+                print(f"\nInferencing: {w}")
+                forced = None
+                phoneme_txt = path.replace(".wav", ".txt")
+                if os.path.exists(phoneme_txt):
+                    forced = []
+                    with open(phoneme_txt, "r", encoding="utf-8") as fh:
+                        for line in fh:
+                            forced.extend(line.strip().split())
+                    print(f"Loaded forced phoneme list with {len(forced)} phonemes.")
+                files.append(_prepare_audio(sess, path, audio, sr, forced))
+            per_file = _label_files(sess, files, lang_id, confidence_threshold)
+            for w, f, segs in zip(names, files, per_file):
+                output_lab_path = os.path.join(output_dir, w.replace(".wav", ".lab"))
+                segments = _finish_file(f, segs, str(output_lab_path))
+                results[w] = segments
+                print("Predicted segments:")
+                for start, end, ph in segments:
+                    print(f"({round(start, 2)}, {round(end, 2)}, {ph})")
+    return results
 
 
 def _cli():
