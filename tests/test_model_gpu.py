@@ -344,3 +344,52 @@ def test_full_size_cfg2_properties():
                                                              o1[b].float().cpu().numpy()), "right")
         assert segs[b] == want
         assert po.merge_adjacent_segments(list(segs[b]), "right") == segs[b]  # merging is idempotent
+
+
+def test_full_size_cfg3_properties():
+    """BASELINE configs[2] at full size (whisper-small + BiLSTM(2) + 4 Conformer + dilated stack, batch 64 x 30 s):
+    determinism, batch invariance (the batch-64 pass runs the BiLSTM with 16 clips per cluster and the GEMMs as CTA
+    pairs, the batch-1 pass with 8 per cluster and single CTAs -- same bits), and an fp32-oracle check on one clip."""
+    from wfl_asr_b200 import synth
+    cfg = synth.workload_config("cfg3")
+    labels = synth.synth_labels(30)
+    model = synth.bench_model(BIOPhonemeTagger, cfg, labels)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    B = 64
+    base = [synth.synth_wave(700 + i, 30.0) for i in range(4)]
+    wave = torch.from_numpy(np.stack([base[i % 4] * (0.5 + 0.5 * ((i * 7) % 11) / 11.0) for i in range(B)]).astype(np.float32))
+    lang = torch.tensor([i % 2 for i in range(B)], device=DEV)
+    l1, o1 = model(wave.to(DEV), lang)
+    l1, o1 = l1.clone(), o1.clone()
+    l2, o2 = model(wave.to(DEV), lang)
+    assert torch.equal(l1, l2) and torch.equal(o1, o2), "forward is not deterministic"
+    for i in (0, 41, 63):
+        li, oi = model(wave[i:i + 1].to(DEV), lang[i:i + 1])
+        assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch 64 and batch 1"
+    ref_l, ref_o = to.forward(wave[41:42], sd, cfg, lang[41:42].cpu())
+    rel, agree, agree_safe, off_err = _compare("cfg3 full size, clip 41", l1[41:42].float().cpu(), o1[41:42].float().cpu(), ref_l, ref_o)
+    assert rel <= 2e-3 and agree_safe == 1.0 and agree >= 0.998
+
+
+def test_encoder_run_to_run_determinism_soak():
+    """Six passes of a whisper-small encoder-only model (d 768: the persistent GEMMs' last round is more than half
+    full, the shape on which an attention -> out-projection programmatic-launch race once made the last clips of a
+    batch differ run to run) must be bitwise identical."""
+    from wfl_asr_b200 import synth
+    cfg = synth.workload_config("cfg3")
+    cfg["model"].update(enable_bilstm=False, enable_dilated_conv=False, num_conformer_layers=0)
+    model = synth.bench_model(BIOPhonemeTagger, cfg, synth.synth_labels(30)).to(DEV).eval()
+    B = 32
+    base = [synth.synth_wave(700 + i, 30.0) for i in range(4)]
+    wave = torch.from_numpy(np.stack([base[i % 4] * (0.5 + 0.5 * ((i * 7) % 11) / 11.0) for i in range(B)]).astype(np.float32)).to(DEV)
+    lang = torch.tensor([i % 2 for i in range(B)], device=DEV)
+    first = None
+    for r in range(6):
+        l, o = model(wave, lang)
+        if first is None:
+            first = (l.clone(), o.clone())
+        else:
+            bad = (l != first[0]).flatten(1).any(dim=1).nonzero().flatten().tolist()
+            assert not bad, f"pass {r} differs from pass 0 in clips {bad}"
+            assert torch.equal(o, first[1])

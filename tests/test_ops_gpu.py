@@ -416,7 +416,8 @@ def test_merge_rejects_bad_mode():
 
 
 # ----------------------------------------------------------------------------------------- BiLSTM
-@pytest.mark.parametrize("H,B,T", [(256, 3, 50), (384, 9, 37), (192, 8, 120), (512, 8, 30), (640, 5, 25)])
+@pytest.mark.parametrize("H,B,T", [(256, 3, 50), (384, 9, 37), (192, 8, 120), (512, 8, 30), (640, 5, 25),
+                                   (384, 64, 12), (256, 70, 9)])  # the last two: 16 batch items per cluster
 def test_lstm_layer(H, B, T):
     """One bidirectional layer vs the step-by-step oracle restatement of nn.LSTM (REF/model.py:105-111)."""
     d = 2 * H

@@ -22,6 +22,8 @@
 // TF/models/wavlm/modeling_wavlm.py:147-241 (additive gated relative position bias).
 #include <type_traits>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wfl {
@@ -142,7 +144,6 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -440,6 +441,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  // Programmatic-launch trigger at the END, after every bulk store of this CTA has completed: with the trigger at the
+  // top of the kernel (where the GEMMs have theirs) the out-projection GEMM that consumes this output through TMA
+  // occasionally read rows of the last CTAs' tiles from the PREVIOUS layer (run-to-run differences in the last
+  // clips of a batch, tools/determinism_check.py) -- griddepcontrol.wait in the consumer did not cover the bulk
+  // async-proxy stores still in flight.  Triggering late costs ~2 us of overlap per attention launch.
+  pdl_launch_dependents();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -479,6 +486,10 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
     configured = true;
   }
   dim3 grid((T + 127) / 128, H, B);
+  {
+    static const bool no_pdl = getenv("WFL_NO_PDL_ATTN") != nullptr;
+    pdl_family_off() = no_pdl;
+  }
   WFL_CUDA(launch_pdl(kern, grid, dim3(kAttnThreads), Cfg::kSmemBytes, stream, mq, mkv, mo, p));
   return WFL_OK;
 }

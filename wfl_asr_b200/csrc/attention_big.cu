@@ -9,6 +9,8 @@
 //     Q is re-read from L2 once per KV tile -- attention is 1-7 % of the FLOPs at these widths, L2 has the bandwidth.
 // The softmax/correction/epilogue warps are the same row-per-thread online softmax with lazy rescaling as in
 // attention.cu (no relative-position bias: large heads only occur in the Conformer blocks).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wfl {
@@ -103,7 +105,6 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -330,6 +331,7 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  pdl_launch_dependents();  // late, after this CTA's bulk stores completed (see attention.cu)
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -368,6 +370,10 @@ static int launch_big(const void* qkv, int64_t row_stride, int64_t batch_stride,
     configured = true;
   }
   dim3 grid((T + 127) / 128, H * 2, B);
+  {
+    static const bool no_pdl = getenv("WFL_NO_PDL_ATTN") != nullptr;
+    pdl_family_off() = no_pdl;
+  }
   WFL_CUDA(launch_pdl(kern, grid, dim3(kBigThreads), Cfg::kSmemBytes, stream, mq, mkv, mo, p));
   return WFL_OK;
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/wfl_b200.h"
 
@@ -45,6 +46,17 @@ int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// per-family switch set by the caller right before a launch (WFL_NO_PDL_GEMM / WFL_NO_PDL_ATTN: bisection aid)
+inline bool& pdl_family_off() {
+  static thread_local bool off = false;
+  return off;
+}
+// WFL_NO_PDL=1 launches everything fully serialised (debugging aid: takes the overlap out of a suspected race)
+inline bool pdl_enabled() {
+  static const bool on = getenv("WFL_NO_PDL") == nullptr;
+  return on && !pdl_family_off();
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                               Args... args) {
@@ -55,7 +67,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
@@ -72,7 +84,7 @@ inline cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 bl
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   attr[1].id = cudaLaunchAttributeClusterDimension;
   attr[1].val.clusterDim.x = cluster_x;
   attr[1].val.clusterDim.y = 1;

@@ -438,6 +438,13 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const GemmParams
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
+  static const bool no_pdl = getenv("WFL_NO_PDL_GEMM") != nullptr;
+  static const int no_pdl_mode = getenv("WFL_NO_PDL_GEMM_MODE") ? atoi(getenv("WFL_NO_PDL_GEMM_MODE")) : -1;
+  // bisection aid: WFL_NO_PDL_GEMM_K=k serialises ADD_F32 launches with K <= k (k > 0) or K > -k (k < 0)
+  static const int no_pdl_k = getenv("WFL_NO_PDL_GEMM_K") ? atoi(getenv("WFL_NO_PDL_GEMM_K")) : 0;
+  const int k_total = p.num_slabs * p.kblocks_per_slab * BK;
+  const bool k_hit = OUT_MODE == WFL_OUT_ADD_F32 && ((no_pdl_k > 0 && k_total <= no_pdl_k) || (no_pdl_k < 0 && k_total > -no_pdl_k));
+  pdl_family_off() = no_pdl || no_pdl_mode == OUT_MODE || k_hit;
   if constexpr (PAIR) {
     int grid = num_sms() & ~1;
     if (grid > 2 * p.total_tiles) grid = 2 * p.total_tiles;

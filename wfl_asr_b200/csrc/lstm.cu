@@ -145,14 +145,16 @@ lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B,
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? s : T - 1 - s;
     const int cur = s & 1, nxt = cur ^ 1;
-    // ---- W_hh h_{t-1} for this warp's 16 gate rows x 2 tiles x NB batch columns over its K half.  Independent
-    // accumulator chains halve the dependent-MMA latency: even / odd k-tiles for NB = 8, the two column tiles for 16.
-    constexpr int kChains = kNT == 1 ? 2 : kNT;
-    float acc_if[kChains][4], acc_go[kChains][4];
+    // ---- W_hh h_{t-1} for this warp's 16 gate rows x 2 tiles x NB batch columns over its K half.  Even and odd
+    // k-tiles accumulate in separate chains (halves the dependent-MMA latency) and are added at the end -- the SAME
+    // summation order for NB = 8 and 16, so a clip's result does not depend on how many clips share its cluster.
+    float acc_if[kNT][2][4], acc_go[kNT][2][4];
 #pragma unroll
-    for (int c = 0; c < kChains; ++c)
+    for (int nt = 0; nt < kNT; ++nt)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc_if[c][i] = acc_go[c][i] = 0.f;
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc_if[nt][c][i] = acc_go[nt][c][i] = 0.f;
     const __half* hrow = hbuf + (cur * kLstmNB + g) * Cfg::kHStride + khalf * Cfg::kKTiles * 16 + 2 * q;
 #pragma unroll
     for (int kt = 0; kt < Cfg::kKTiles; ++kt) {
@@ -160,24 +162,23 @@ lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B,
       for (int nt = 0; nt < kNT; ++nt) {
         const uint32_t hb0 = *reinterpret_cast<const uint32_t*>(hrow + nt * 8 * Cfg::kHStride + kt * 16);
         const uint32_t hb1 = *reinterpret_cast<const uint32_t*>(hrow + nt * 8 * Cfg::kHStride + kt * 16 + 8);
-        const int c = kNT == 1 ? (kt & 1) : nt;
-        mma_f16_16816(acc_if[c], wa[kt], hb0, hb1);
-        mma_f16_16816(acc_go[c], wb[kt], hb0, hb1);
+        mma_f16_16816(acc_if[nt][kt & 1], wa[kt], hb0, hb1);
+        mma_f16_16816(acc_go[nt][kt & 1], wb[kt], hb0, hb1);
       }
     }
-    if constexpr (kNT == 1) {
+#pragma unroll
+    for (int nt = 0; nt < kNT; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        acc_if[0][i] += acc_if[1][i];
-        acc_go[0][i] += acc_go[1][i];
+        acc_if[nt][0][i] += acc_if[nt][1][i];
+        acc_go[nt][0][i] += acc_go[nt][1][i];
       }
-    }
     if (khalf == 1) {
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) {
         float4* pp = reinterpret_cast<float4*>(part + ((group * kNT + nt) * 32 + lane) * 8);
-        pp[0] = make_float4(acc_if[nt][0], acc_if[nt][1], acc_if[nt][2], acc_if[nt][3]);
-        pp[1] = make_float4(acc_go[nt][0], acc_go[nt][1], acc_go[nt][2], acc_go[nt][3]);
+        pp[0] = make_float4(acc_if[nt][0][0], acc_if[nt][0][1], acc_if[nt][0][2], acc_if[nt][0][3]);
+        pp[1] = make_float4(acc_go[nt][0][0], acc_go[nt][0][1], acc_go[nt][0][2], acc_go[nt][0][3]);
       }
     }
     __syncthreads();
@@ -206,10 +207,10 @@ lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B,
         const float4 p_if = pp[0], p_go = pp[1];
         const float4 in0 = in[nt][0], in1 = in[nt][1];
         // accumulator layout: [0],[1] = first gate of the tile (rows g) for batch 2q, 2q+1; [2],[3] = second gate (rows g+8)
-        const float ai0 = acc_if[nt][0] + p_if.x + in0.x, ai1 = acc_if[nt][1] + p_if.y + in1.x;
-        const float af0 = acc_if[nt][2] + p_if.z + in0.y, af1 = acc_if[nt][3] + p_if.w + in1.y;
-        const float ag0 = acc_go[nt][0] + p_go.x + in0.z, ag1 = acc_go[nt][1] + p_go.y + in1.z;
-        const float ao0 = acc_go[nt][2] + p_go.z + in0.w, ao1 = acc_go[nt][3] + p_go.w + in1.w;
+        const float ai0 = acc_if[nt][0][0] + p_if.x + in0.x, ai1 = acc_if[nt][0][1] + p_if.y + in1.x;
+        const float af0 = acc_if[nt][0][2] + p_if.z + in0.y, af1 = acc_if[nt][0][3] + p_if.w + in1.y;
+        const float ag0 = acc_go[nt][0][0] + p_go.x + in0.z, ag1 = acc_go[nt][0][1] + p_go.y + in1.z;
+        const float ao0 = acc_go[nt][0][2] + p_go.z + in0.w, ao1 = acc_go[nt][0][3] + p_go.w + in1.w;
         c_state[nt][0] = sigmoid_acc(af0) * c_state[nt][0] + sigmoid_acc(ai0) * tanh_acc(ag0);
         c_state[nt][1] = sigmoid_acc(af1) * c_state[nt][1] + sigmoid_acc(ai1) * tanh_acc(ag1);
         const float h0 = sigmoid_acc(ao0) * tanh_acc(c_state[nt][0]);
