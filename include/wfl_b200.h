@@ -112,8 +112,11 @@ int wfl_layernorm(const float* x, int64_t rows, int32_t d, const float* gamma, c
  * T0 = (n_samples-10)/5+1 frames of each clip; norm_mode 1: zero-mean/unit-variance waveform
  * (TF/models/wav2vec2/feature_extraction_wav2vec2.py:77-97) then LayerNorm over channels} + GELU.
  * wave fp32 [B][wave_stride]; w fp32 [512][10]; out f16 [B][out_batch_stride] rows of 512 channels.
- * scratch_stats: (2 + 1024) * B doubles.  The pre-norm activations are recomputed, never stored.
+ * scratch_stats: WFL_WAVLM_STATS_DOUBLES doubles per clip (final statistics + per-block partial sums: the statistics
+ * are reduced in a fixed order, no floating-point atomics, so results are bitwise reproducible and independent of
+ * the batch).  The pre-norm activations are recomputed, never stored.
  */
+#define WFL_WAVLM_STATS_DOUBLES 131072
 int wfl_wavlm_conv0(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, const float* w,
                     const float* gamma, const float* beta, int32_t norm_mode, void* out_f16,
                     int64_t out_batch_stride, double* scratch_stats, void* stream);

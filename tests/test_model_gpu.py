@@ -374,8 +374,8 @@ def test_full_size_cfg3_properties():
 
 def test_encoder_run_to_run_determinism_soak():
     """Six passes of a whisper-small encoder-only model (d 768: the persistent GEMMs' last round is more than half
-    full, the shape on which an attention -> out-projection programmatic-launch race once made the last clips of a
-    batch differ run to run) must be bitwise identical."""
+    full, the shape on which a barrier-phase race in the attention kernel once made the last clips of a batch differ
+    run to run) must be bitwise identical."""
     from wfl_asr_b200 import synth
     cfg = synth.workload_config("cfg3")
     cfg["model"].update(enable_bilstm=False, enable_dilated_conv=False, num_conformer_layers=0)

@@ -199,6 +199,26 @@ def test_attention(hd, H, T, B):
     _report(f"attention hd{hd}", out, ref, 2e-2)
 
 
+@pytest.mark.parametrize("bias", [False, True])
+def test_attention_run_to_run_determinism(bias):
+    """120 launches on fixed inputs must be bitwise identical (the WavLM-bias launches once were not: rows 96..127 of
+    random query tiles changed in ~7 % of launches: a fast lane quarter's p_full arrival for tile j+2 completed the
+    slow quarter's phase for tile j)."""
+    B, T, H, hd = 16, 1499, 16, 64
+    d = H * hd
+    qkv = _rand(B, T, 3 * d, scale=0.5, seed=71).half()
+    rel = _rand(H, 2 * T - 1, seed=72) if bias else None
+    gate = (1.0 + 0.3 * _rand(B, H, T, seed=73)) if bias else None
+    out = torch.empty(B, T, d, device=DEV, dtype=torch.float16)
+    ref = None
+    for it in range(120):
+        ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=hd ** -0.5, q_col=0, k_col=d, v_col=2 * d, rel_bias=rel, gate=gate)
+        if ref is None:
+            ref = out.clone()
+        else:
+            assert torch.equal(out.view(torch.int16), ref.view(torch.int16)), f"launch {it} differs from launch 0"
+
+
 def test_attention_peaky_scores_rescale():
     """Large score range forces the lazy O-rescale path (running max grows by > 2^8 between tiles)."""
     hd, H, T, B = 64, 2, 700, 1

@@ -36,7 +36,7 @@ int attention_big_dispatch(const void* qkv, int64_t row_stride, int64_t batch_st
 // (tcgen05.st by the softmax warps, A-from-TMEM MMA).  At hd 64 the kernel was shared-memory-bandwidth bound: per
 // 64-key tile the MMAs read Q 16 KB + K 8 KB + P 16 KB + V 8 KB and the softmax wrote P 16 KB; this removes 32 KB.
 // false = stage P in 128B-swizzled shared memory (A-from-smem MMA).
-constexpr bool kPTmem = true;
+
 constexpr int kAttnThreads = 384;
 constexpr int kKvTile = 64;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -56,7 +56,7 @@ __device__ __forceinline__ void pair_sync(int quarter) {
   asm volatile("bar.sync %0, 64;" ::"r"(quarter + 2) : "memory");
 }
 
-template <int HD, int KV_STAGES>
+template <int HD, int KV_STAGES, bool kPTmem>
 struct AttnCfg {
   static constexpr int kHdBlocks = HD / 64;
   static constexpr int kQBytes = 128 * HD * 2;
@@ -83,11 +83,11 @@ struct AttnParams {
   const float* gate;      // [B][H][T] or null
 };
 
-template <int HD, int KV_STAGES>
-__global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES>::kCtasPerSm))
+template <int HD, int KV_STAGES, bool kPTmem>
+__global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES, kPTmem>::kCtasPerSm))
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                  const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
-  using Cfg = AttnCfg<HD, KV_STAGES>;
+  using Cfg = AttnCfg<HD, KV_STAGES, kPTmem>;
   constexpr int KV_TILE = kKvTile;
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (128B swizzle); checked below
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -144,6 +144,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -339,10 +340,12 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           }
           m_used = m_new;
         }
-        if constexpr (!kPTmem) {
-          // the smem P buffer we are about to overwrite was read by PV(j-2)
-          if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
-        }
+        // PV(j-2) must have retired before this warp publishes P_j: it used the same p_full / pv_done pair (sb = j & 1).
+        // Shared-memory P: its buffer is about to be overwritten.  TMEM P: the S ring lets a fast lane quarter run two
+        // tiles ahead of a slow one, and without this wait its arrival for tile j+2 lands in p_full[sb]'s phase for
+        // tile j -- that phase then completes with the slow quarter's P_j still unwritten and PV(j) reads stale rows
+        // (seen as run-to-run differences in rows 96..127 of random query tiles, tools/attn_determinism.py).
+        if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
 
         // P = 2^(x - m_used) -> f16 -> swizzled smem; row sum in fp32
         const float neg_m = -m_used;
@@ -441,23 +444,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  // Programmatic-launch trigger at the END, after every bulk store of this CTA has completed: with the trigger at the
-  // top of the kernel (where the GEMMs have theirs) the out-projection GEMM that consumes this output through TMA
-  // occasionally read rows of the last CTAs' tiles from the PREVIOUS layer (run-to-run differences in the last
-  // clips of a batch, tools/determinism_check.py) -- griddepcontrol.wait in the consumer did not cover the bulk
-  // async-proxy stores still in flight.  Triggering late costs ~2 us of overlap per attention launch.
-  pdl_launch_dependents();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int HD, int KV_STAGES>
+template <int HD, int KV_STAGES, bool kPTmem>
 static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int B, int T, int H,
                             const AttnParams& p, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                             cudaStream_t stream) {
-  using Cfg = AttnCfg<HD, KV_STAGES>;
+  using Cfg = AttnCfg<HD, KV_STAGES, kPTmem>;
   CUtensorMap mq, mkv, mo;
   {
     uint64_t dims[3] = {(uint64_t)row_stride, (uint64_t)T, (uint64_t)B};  // any column of the row may be addressed
@@ -479,7 +476,7 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = attention_kernel<HD, KV_STAGES>;
+  auto kern = attention_kernel<HD, KV_STAGES, kPTmem>;
   static bool configured = false;
   if (!configured) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -521,21 +518,23 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
   p.gate = gate;
   switch (hd) {
     case 64:
-      return launch_attention<64, 3>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride,
-                                     stream);
+      return launch_attention<64, 3, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+                                           out_batch_stride, stream);
     case 256:
-      return launch_attention<256, 2>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride,
-                                      stream);
+      if (rel_bias != nullptr) break;
+      return launch_attention<256, 2, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+                                            out_batch_stride, stream);
     case 384:
-      return launch_attention<384, 1>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride,
-                                      stream);
+      if (rel_bias != nullptr) break;
+      return launch_attention<384, 1, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+                                            out_batch_stride, stream);
     default:
-      if (rel_bias != nullptr) {
-        set_error("wfl_attention: relative-position bias is only built for head_dim 64/256/384 (got %d)", hd);
-        return WFL_ERR_UNSUPPORTED;
-      }
+      if (rel_bias != nullptr) break;
       // head_dim 512 / 640: streamed-Q, split-V variant (attention_big.cu)
       return attention_big_dispatch(qkv, row_stride, batch_stride, q_col, k_col, v_col, B, T, H, hd, scale, out,
                                     out_row_stride, out_batch_stride, stream);
   }
+  // the WavLM encoders (the only users of the bias) have head_dim 64
+  set_error("wfl_attention: the gated relative-position bias is built for head_dim 64 only (got %d)", hd);
+  return WFL_ERR_UNSUPPORTED;
 }

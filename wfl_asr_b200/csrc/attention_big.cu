@@ -105,6 +105,7 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -331,7 +332,6 @@ attention_big_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  pdl_launch_dependents();  // late, after this CTA's bulk stores completed (see attention.cu)
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

@@ -33,9 +33,15 @@ __device__ __forceinline__ float gelu_exact(float v) {
   return v * (v >= 0.0f ? 1.0f - h : h);
 }
 
-// per-clip sum and sum of squares of the waveform (double accumulators; clip_stats[b] = {sum, sumsq})
+// Statistics are reduced in a FIXED order (per-block partial sums in scratch, then one ordered pass) instead of with
+// floating-point atomics, so a clip's result does not depend on scheduling or on what else is in the batch.
+constexpr int kWaveStatBlocks = 64;   // partial sums per clip for the waveform statistics
+constexpr int kStatTilesPerBlock = 16;  // conv0 statistics: 16 tiles of 64 frames per block
+
+// per-clip sum and sum of squares of the waveform (double accumulators): parts[b][block] = {sum, sumsq}
 __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ wave, int64_t stride, int n,
-                                                         double* __restrict__ clip_stats) {
+                                                         double* __restrict__ parts) {
+  __shared__ double red[2][8];
   const int b = blockIdx.y;
   const float* w = wave + b * stride;
   double s = 0.0, q = 0.0;
@@ -50,9 +56,41 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(clip_stats + 2 * b, s);
-    atomicAdd(clip_stats + 2 * b + 1, q);
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = q;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      ts += red[0][i];
+      tq += red[1][i];
+    }
+    parts[(static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * 2] = ts;
+    parts[(static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * 2 + 1] = tq;
+  }
+}
+// clip_stats[b] = ordered sum of its partials
+__global__ void clip_stats_finish_kernel(const double* __restrict__ parts, int n_parts, double* __restrict__ clip_stats) {
+  const int b = blockIdx.x;
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int i = 0; i < n_parts; ++i) t += parts[(static_cast<int64_t>(b) * n_parts + i) * 2 + threadIdx.x];
+    clip_stats[2 * b + threadIdx.x] = t;
+  }
+}
+// ch_stats[b][c] = ordered sum over the stat blocks of ch_parts[b][block][c]
+__global__ void __launch_bounds__(kC0) ch_stats_finish_kernel(const double* __restrict__ ch_parts, int n_parts,
+                                                              double* __restrict__ ch_stats) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < n_parts; ++i) {
+    const double* p = ch_parts + ((static_cast<int64_t>(b) * n_parts + i) * kC0 + c) * 2;
+    s += p[0];
+    q += p[1];
+  }
+  ch_stats[(static_cast<int64_t>(b) * kC0 + c) * 2] = s;
+  ch_stats[(static_cast<int64_t>(b) * kC0 + c) * 2 + 1] = q;
 }
 
 // mode 0: accumulate per-(clip, channel) sum / sumsq of the conv output (GroupNorm statistics)
@@ -69,8 +107,16 @@ __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wa
   __shared__ float xs[kC0Frames * kC0Stride + kC0Taps];
   __shared__ float red[2][16];
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * kC0Frames;
   const int c = threadIdx.x;
+  // MODE 0 (statistics) walks kStatTilesPerBlock consecutive 64-frame tiles and emits ONE partial sum per channel
+  constexpr int kTiles = MODE == 0 ? kStatTilesPerBlock : 1;
+  float s_acc = 0.f, q_acc = 0.f;
+  double s_tot = 0.0, q_tot = 0.0;
+#pragma unroll 1
+  for (int tile = 0; tile < kTiles; ++tile) {
+  const int t0 = (blockIdx.x * kTiles + tile) * kC0Frames;
+  if (t0 >= T0) break;
+  if (tile > 0) __syncthreads();  // the previous tile's window is no longer read
   const int nt = min(kC0Frames, T0 - t0);
   // optional zero-mean / unit-variance input (fp32 like the numpy reference)
   float mu = 0.f, rs = 1.f;
@@ -101,7 +147,8 @@ __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wa
     rstd_c = 1.0f / sqrtf(static_cast<float>(q / T0 - m * m) + 1e-5f);
   }
   __syncthreads();
-  float s_acc = 0.f, q_acc = 0.f;
+  s_acc = 0.f;
+  q_acc = 0.f;
   for (int f = 0; f < nt; ++f) {
     float y = 0.f;
 #pragma unroll
@@ -132,9 +179,15 @@ __global__ void __launch_bounds__(kC0) conv0_kernel(const float* __restrict__ wa
       out[b * out_batch_stride + static_cast<int64_t>(t0 + f) * kC0 + c] = to_f16(gelu_exact(v));
     }
   }
-  if (MODE == 0) {
-    atomicAdd(ch_stats + (static_cast<int64_t>(b) * kC0 + c) * 2, static_cast<double>(s_acc));
-    atomicAdd(ch_stats + (static_cast<int64_t>(b) * kC0 + c) * 2 + 1, static_cast<double>(q_acc));
+  if (MODE == 0) {  // fp32 within a 64-frame tile (as before), fp64 across tiles
+    s_tot += static_cast<double>(s_acc);
+    q_tot += static_cast<double>(q_acc);
+  }
+  }  // tile loop
+  if (MODE == 0) {  // ch_stats is the PARTIALS buffer here: [B][gridDim.x][512][2]
+    double* p = ch_stats + ((static_cast<int64_t>(b) * gridDim.x + blockIdx.x) * kC0 + c) * 2;
+    p[0] = s_tot;
+    p[1] = q_tot;
   }
 }
 
@@ -186,21 +239,28 @@ extern "C" int wfl_wavlm_conv0(const float* wave, int64_t wave_stride, int32_t n
   WFL_CHECK_ARG(out_batch_stride >= static_cast<int64_t>(T0) * kC0, "wfl_wavlm_conv0: out_batch_stride too small");
   dim3 grid((T0 + kC0Frames - 1) / kC0Frames, B);
   __half* out = static_cast<__half*>(out_f16);
+  // scratch layout (WFL_WAVLM_STATS_DOUBLES doubles per clip): final statistics, then the per-block partials
   double* clip_stats = scratch_stats;            // [B][2]
   double* ch_stats = scratch_stats + 2 * B;      // [B][512][2]
+  double* parts = ch_stats + 2 * kC0 * static_cast<int64_t>(B);
   if (norm_mode == 0) {
-    // wavlm-base(-plus): raw waveform in, GroupNorm statistics over time, then apply
-    WFL_CUDA(cudaMemsetAsync(ch_stats, 0, sizeof(double) * 2 * kC0 * B, stream));
-    conv0_kernel<0><<<grid, kC0, 0, stream>>>(wave, wave_stride, n_samples, T0, w, gamma, beta, clip_stats, 0, ch_stats,
-                                              out, out_batch_stride);
+    // wavlm-base(-plus): raw waveform in, GroupNorm statistics over time (ordered two-level sum), then apply
+    const int stat_blocks = (static_cast<int>(grid.x) + kStatTilesPerBlock - 1) / kStatTilesPerBlock;
+    WFL_CHECK_ARG(2 + 2 * kC0 + 2LL * kC0 * stat_blocks <= WFL_WAVLM_STATS_DOUBLES,
+                  "wfl_wavlm_conv0: clip of %d samples needs more statistics scratch than WFL_WAVLM_STATS_DOUBLES", n_samples);
+    conv0_kernel<0><<<dim3(stat_blocks, B), kC0, 0, stream>>>(wave, wave_stride, n_samples, T0, w, gamma, beta, clip_stats,
+                                                             0, parts, out, out_batch_stride);
+    WFL_CUDA(cudaGetLastError());
+    ch_stats_finish_kernel<<<B, kC0, 0, stream>>>(parts, stat_blocks, ch_stats);
     WFL_CUDA(cudaGetLastError());
     conv0_kernel<1><<<grid, kC0, 0, stream>>>(wave, wave_stride, n_samples, T0, w, gamma, beta, clip_stats, 0, ch_stats,
                                               out, out_batch_stride);
   } else {
     // wavlm-large: zero-mean/unit-variance waveform, LayerNorm over channels per frame
-    WFL_CUDA(cudaMemsetAsync(clip_stats, 0, sizeof(double) * 2 * B, stream));
-    dim3 g1(64, B);
-    wave_stats_kernel<<<g1, 256, 0, stream>>>(wave, wave_stride, n_samples, clip_stats);
+    dim3 g1(kWaveStatBlocks, B);
+    wave_stats_kernel<<<g1, 256, 0, stream>>>(wave, wave_stride, n_samples, parts);
+    WFL_CUDA(cudaGetLastError());
+    clip_stats_finish_kernel<<<B, 32, 0, stream>>>(parts, kWaveStatBlocks, clip_stats);
     WFL_CUDA(cudaGetLastError());
     conv0_kernel<2><<<grid, kC0, 0, stream>>>(wave, wave_stride, n_samples, T0, w, gamma, beta, clip_stats, 1, ch_stats,
                                               out, out_batch_stride);

@@ -236,7 +236,7 @@ class Engine:
             ws["cB"] = torch.empty(B * Ts[1] + 2, 512, **bf)
             ws["cf"] = torch.empty(B * (Ts[1] if large else Ts[6]), 512, device=dev)
             ws["h512"] = torch.empty(M, 512, **bf)
-            ws["wstats"] = torch.empty((2 + 1024) * B, dtype=torch.float64, device=dev)
+            ws["wstats"] = torch.empty(ops.WAVLM_STATS_DOUBLES * B, dtype=torch.float64, device=dev)
             ws["gate"] = torch.empty(B, self.arch["heads"], T, device=dev)
         self._ws = {key: ws}  # keep one shape resident (batches of one shape dominate bulk labeling)
         return ws

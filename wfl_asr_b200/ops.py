@@ -93,6 +93,9 @@ def layernorm(x, gamma, beta, *, out_f32=None, out_f16=None, gamma2=None, beta2=
     _count()
 
 
+WAVLM_STATS_DOUBLES = 131072  # include/wfl_b200.h WFL_WAVLM_STATS_DOUBLES (doubles of scratch per clip)
+
+
 def wavlm_conv0(wave, n_samples, w, gamma, beta, norm_mode, out, out_batch_stride, scratch):
     """wave fp32 [B, >=n_samples] -> out f16 [B, out_batch_stride/512 rows, 512] (conv k10 s5 + norm + GELU)."""
     rc = _lib.load().wfl_wavlm_conv0(_ptr(wave), wave.stride(0), n_samples, wave.shape[0], _ptr(w), _ptr(gamma),
