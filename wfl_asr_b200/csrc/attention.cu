@@ -83,7 +83,7 @@ struct AttnParams {
   const float* gate;      // [B][H][T] or null
 };
 
-template <int HD, int KV_STAGES, bool kPTmem>
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias>
 __global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES, kPTmem>::kCtasPerSm))
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                  const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
@@ -266,7 +266,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const int r = quarter * 32 + lane;     // query row inside the tile == TMEM lane
     const int q_idx = q0 + r;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const bool has_bias = p.rel_bias != nullptr;
+    constexpr bool has_bias = kHasBias;  // compile-time: the plain kernel does not carry the bias path's registers
     float gate_l2 = 0.f;
     const float* bias_row = nullptr;
     if (has_bias) {
@@ -385,13 +385,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         l_sum += (sum[0] + sum[1]) + (sum[2] + sum[3]);
       };
       const bool tail = (j + 1) * KV_TILE > p.T;  // CTA-uniform
-      if (has_bias) {
-        if (tail) tile(std::true_type{}, std::true_type{});
-        else tile(std::true_type{}, std::false_type{});
-      } else {
-        if (tail) tile(std::false_type{}, std::true_type{});
-        else tile(std::false_type{}, std::false_type{});
-      }
+      if (tail) tile(std::integral_constant<bool, kHasBias>{}, std::true_type{});
+      else tile(std::integral_constant<bool, kHasBias>{}, std::false_type{});
 #else
       l_sum = 1.0f;
       (void)kv0;
@@ -450,7 +445,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 }
 
-template <int HD, int KV_STAGES, bool kPTmem>
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias>
 static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int B, int T, int H,
                             const AttnParams& p, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                             cudaStream_t stream) {
@@ -476,7 +471,7 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = attention_kernel<HD, KV_STAGES, kPTmem>;
+  auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias>;
   static bool configured = false;
   if (!configured) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -518,15 +513,18 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
   p.gate = gate;
   switch (hd) {
     case 64:
-      return launch_attention<64, 3, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
-                                           out_batch_stride, stream);
+      if (rel_bias != nullptr)
+        return launch_attention<64, 3, true, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+                                                   out_batch_stride, stream);
+      return launch_attention<64, 3, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+                                                  out_batch_stride, stream);
     case 256:
       if (rel_bias != nullptr) break;
-      return launch_attention<256, 2, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+      return launch_attention<256, 2, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                             out_batch_stride, stream);
     case 384:
       if (rel_bias != nullptr) break;
-      return launch_attention<384, 1, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+      return launch_attention<384, 1, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                             out_batch_stride, stream);
     default:
       if (rel_bias != nullptr) break;
