@@ -289,30 +289,32 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       tmem_ld32(lane_addr + ss * KV_TILE + ch * 32, v);
       tmem_ld_wait();
 
-      // One tile of online softmax, specialised on (relative-position bias, partial last tile) so the common
-      // case costs one FMNMX, then FFMA + MUFU.EX2 + FADD + half a CVT per score.
-      auto tile = [&](auto bias_c, auto tail_c) {
+      // One tile of online softmax.  The scores are brought to ONE form in place in v[] -- raw accumulator bits, to be
+      // multiplied by `sc` -- so that the hot part (one FMNMX, then FFMA + MUFU.EX2 + FADD + half a CVT per score) is the
+      // same code for every case and no second score array lives in registers:
+      //   plain:  v = S,                       sc = scale * log2 e       (scale > 0: max commutes with the scaling)
+      //   bias:   v = S * sc0 + gate * bias,   sc = 1
+      //   the partial last tile masks keys >= T with -inf first.
+      const bool tail = (j + 1) * KV_TILE > p.T;  // CTA-uniform
+      auto tile = [&](auto bias_c) {
         constexpr bool kBias = decltype(bias_c)::value;
-        constexpr bool kTail = decltype(tail_c)::value;
-        float x[32];  // scores in log2 units (general path only)
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        const float sc = kBias ? 1.0f : p.scale_log2;
+        if constexpr (kBias) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if constexpr (!kBias && !kTail) {
-            mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(v[i]));  // scale > 0: max commutes with the scaling
-          } else {
-            const int k = kv0 + i;
-            float s = __uint_as_float(v[i]) * p.scale_log2;
-            if constexpr (kBias) {
-              if (!kTail || k < p.T) s = fmaf(gate_l2, __ldg(bias_row + k), s);
-            }
-            if constexpr (kTail) s = k < p.T ? s : -INFINITY;
-            x[i] = s;
-            mx[i & 3] = fmaxf(mx[i & 3], s);
+          for (int i = 0; i < 32; ++i) {
+            const int k = min(kv0 + i, p.T - 1);
+            v[i] = __float_as_uint(fmaf(gate_l2, __ldg(bias_row + k), __uint_as_float(v[i]) * p.scale_log2));
           }
         }
-        float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        if constexpr (!kBias && !kTail) m_half *= p.scale_log2;
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + i >= p.T) v[i] = 0xff800000u;  // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(v[i]));
+        const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc;
         // combine with the warp that owns the other 32 columns of these rows
         float* xm = xmax + (sb * 2) * 128;
         xm[ch * 128 + r] = m_half;
@@ -353,14 +355,8 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float e0, e1;
-          if constexpr (!kBias && !kTail) {
-            e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-            e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, neg_m));
-          } else {
-            e0 = ex2_approx(x[i] + neg_m);
-            e1 = ex2_approx(x[i + 1] + neg_m);
-          }
+          const float e0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
           sum[(i >> 1) & 3] += e0 + e1;
           pk[i >> 1] = pack_f16(e0, e1);
         }
@@ -384,9 +380,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         l_sum += (sum[0] + sum[1]) + (sum[2] + sum[3]);
       };
-      const bool tail = (j + 1) * KV_TILE > p.T;  // CTA-uniform
-      if (tail) tile(std::integral_constant<bool, kHasBias>{}, std::true_type{});
-      else tile(std::integral_constant<bool, kHasBias>{}, std::false_type{});
+      tile(std::integral_constant<bool, kHasBias>{});
 #else
       l_sum = 1.0f;
       (void)kv0;
