@@ -351,12 +351,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
         // P = 2^(x - m_used) -> f16 -> swizzled smem; row sum in fp32
         const float neg_m = -m_used;
+        const uint64_t sc2 = pk2(sc, sc), negm2 = pk2(neg_m, neg_m);
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+          float a0, a1;
+          upk2(fma2(pk2u(v[i], v[i + 1]), sc2, negm2), a0, a1);  // one FFMA2 for the pair
+          const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
           sum[(i >> 1) & 3] += e0 + e1;
           pk[i >> 1] = pack_f16(e0, e1);
         }
