@@ -277,25 +277,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int n0 = n_tile * BN;  // column inside the group
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      // bias tile -> smem (double-buffered by accumulator stage; written by epilogue warp 0 and 4's lanes), pre-combined
-      // with what the epilogue multiplies it by: alpha (residual add) or -log2(e) (the GLU gate's sigmoid exponent)
+      // Bias for this warp's columns -> smem (double-buffered by accumulator stage), pre-combined with what the epilogue
+      // multiplies it by: alpha (residual add) or -log2(e) (the GLU gate's sigmoid exponent).  Every warp fetches the
+      // values of ITS columns itself (one float4 per lane, requested before the accumulator wait so the L2 latency
+      // hides behind it) and writes them after the wait; the four warps that share a column half write identical
+      // bits, so no cross-warp barrier is needed -- a 256-thread bar.sync per tile was 8 % of the epilogue's samples.
+      // Safe to overwrite: tmem_full for this tile implies every warp released this stage two tiles ago, and a
+      // warp's last bias read of a tile precedes its release.
       float* bsm = bias_smem + acc * BN;
-      if ((ew & 3) == 0) {
-        for (int i = lane + half * (BN / 2); i < (half + 1) * (BN / 2); i += 32) {
-          const int n = n0 + i;
-          float bv = (p.bias != nullptr && n < p.n) ? __ldg(p.bias + b * p.bias_batch_stride + group * p.n + n) : 0.0f;
-          if constexpr (OUT_MODE == WFL_OUT_ADD_F32) bv *= p.alpha;
-          if constexpr (kGlu) {
-            if (i >= BN / 2) bv *= -kLog2e;
-          }
-          bsm[i] = bv;
-        }
-      }
-      // all 8 epilogue warps: bias visible before use (named barrier 1, 256 threads)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      int bcol = half * kColsPerWarp + lane * 4;                       // value columns of this warp
+      if constexpr (kGlu) bcol = lane < 16 ? half * kColsPerWarp + lane * 4 : BN / 2 + half * kColsPerWarp + (lane - 16) * 4;
+      const bool bvalid = kGlu ? (lane & 15) * 4 < kColsPerWarp : lane * 4 < kColsPerWarp;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bvalid && p.bias != nullptr && n0 + bcol < p.n)
+        bv = __ldg(reinterpret_cast<const float4*>(p.bias + b * p.bias_batch_stride + group * p.n + n0 + bcol));
+      float bscale = 1.0f;
+      if constexpr (OUT_MODE == WFL_OUT_ADD_F32) bscale = p.alpha;
+      if constexpr (kGlu) bscale = lane >= 16 ? -kLog2e : 1.0f;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (bvalid) *reinterpret_cast<float4*>(bsm + bcol) = make_float4(bv.x * bscale, bv.y * bscale, bv.z * bscale, bv.w * bscale);
+      __syncwarp();
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       uint8_t* gbox = p.out + b * p.out_batch_bytes + static_cast<long long>(t0 + quarter * 32) * p.out_row_bytes +
                       group * p.out_group_bytes;
@@ -470,6 +473,8 @@ extern "C" int wfl_gemm(const wfl_gemm_desc* d, void* stream_) {
                 d->slab_k, BK);
   WFL_CHECK_ARG(d->n > 0 && d->n % 8 == 0, "wfl_gemm: n %d must be a positive multiple of 8", d->n);
   WFL_CHECK_ARG(d->batches >= 1 && d->m_rows >= 1 && d->a_rows >= 1, "wfl_gemm: empty problem");
+  WFL_CHECK_ARG(d->bias == nullptr || ((reinterpret_cast<uintptr_t>(d->bias) & 15) == 0 && d->bias_batch_stride % 4 == 0),
+                "wfl_gemm: bias must be 16-byte aligned (per-batch stride a multiple of 4 floats)");
   WFL_CHECK_ARG(d->a_row_stride % 8 == 0 && d->a_batch_stride % 8 == 0 && d->a_cols % 8 == 0,
                 "wfl_gemm: A strides/cols must be multiples of 8 elements (16 bytes)");
   WFL_CHECK_ARG((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
