@@ -176,7 +176,8 @@ int wfl_resample_sinc(const double* x, int64_t n_in, int32_t orig, int32_t new_r
  * W[n][k] = hann[k] * {cos, -sin}(2 pi (n/2) k / 400) for output column n (cos/-sin interleaved per bin), zero padded.
  * Then power, mel (filters fp32 [201][n_mels]), log10(clamp 1e-10), per-clip max-8 floor, (x+4)/4.
  * out f16 [B][3000][out_stride] (channels >= n_mels zeroed).  scratch_planes: f16 2*480480*B + 4096 elements;
- * scratch_dft: fp32 [B][3000][448]; scratch_logspec: fp32 [B][3000][n_mels]; scratch_max: B floats.
+ * scratch_dft: fp32 [B][3000][448]; scratch_logspec: fp32 [B][3000][n_mels]; scratch_max: B + 258 floats
+ * (per-clip maxima, then the non-zero bin span of every mel filter).
  */
 int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B,
                        const void* basis_split_f16, const float* mel_filters, int32_t n_mels, void* out_f16,

@@ -148,11 +148,11 @@ def resample_sinc(x_f64, orig, new, width, bank, out_f64):
 
 
 def logmel_scratch(B, n_mels, device):
-    """Scratch buffers of wfl_whisper_logmel: (planes f16, dft fp32 [B,3000,448], logspec fp32, clip max)."""
+    """Scratch buffers of wfl_whisper_logmel: (planes f16, dft fp32 [B,3000,448], logspec fp32, clip max + filter spans)."""
     from .frontend import PLANE_SAMPLES
     return (torch.empty(2 * PLANE_SAMPLES * B + 4096, dtype=torch.float16, device=device),
             torch.empty(B, 3000, 448, device=device), torch.empty(B, 3000, n_mels, device=device),
-            torch.empty(B, device=device))
+            torch.empty(B + 258, device=device))
 
 
 def whisper_logmel(wave, n_samples, basis_split, filters, n_mels, out, scratch):
