@@ -100,6 +100,8 @@ __device__ __forceinline__ double seg_time(int idx, const float* off, int which,
   return __dmul_rn(__dadd_rn(static_cast<double>(idx), o), fd);
 }
 
+constexpr int kBioMaxLabelsSmem = 1024;
+
 __global__ void __launch_bounds__(32) bio_decode_kernel(const int32_t* __restrict__ ids, const float* __restrict__ offsets,
                                                         const int32_t* __restrict__ lengths, int64_t clip_stride,
                                                         const int8_t* __restrict__ label_kind,
@@ -120,15 +122,27 @@ __global__ void __launch_bounds__(32) bio_decode_kernel(const int32_t* __restric
   int count = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 
+  // The loop is a serial chain over groups of 32 frames; its only long-latency part is ids -> label tables.  The
+  // tables are staged in shared memory (when they fit) and the ids of the NEXT group are requested one iteration early.
+  __shared__ int8_t kind_sm[kBioMaxLabelsSmem];
+  __shared__ int32_t ph_sm[kBioMaxLabelsSmem];
+  const bool tables_in_smem = n_labels <= kBioMaxLabelsSmem;
+  if (tables_in_smem) {
+    for (int l = lane; l < n_labels; l += 32) {
+      kind_sm[l] = label_kind[l];
+      ph_sm[l] = label_ph[l];
+    }
+    __syncwarp();
+  }
+  int id_next = lane < T ? cid[lane] : -1;
   for (int g0 = 0; g0 < T; g0 += 32) {
     const int i = g0 + lane;
+    const int id = id_next;
+    id_next = i + 32 < T ? cid[i + 32] : -1;
     int kind = WFL_TAG_OTHER, ph = -1;
-    if (i < T) {
-      const int id = cid[i];
-      if (id >= 0 && id < n_labels) {
-        kind = label_kind[id];
-        ph = label_ph[id];
-      }
+    if (i < T && id >= 0 && id < n_labels) {
+      kind = tables_in_smem ? kind_sm[id] : label_kind[id];
+      ph = tables_in_smem ? ph_sm[id] : label_ph[id];
     }
     const int ph_eff = (kind == WFL_TAG_O || kind == WFL_TAG_OTHER) ? -1 : ph;
     const unsigned m_valid = __ballot_sync(0xffffffffu, kind != WFL_TAG_OTHER);
