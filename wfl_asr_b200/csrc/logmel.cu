@@ -199,7 +199,7 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
     d.m_rows = kFrames;
     d.out_row_stride = kDftCols;
     d.out_batch_stride = static_cast<int64_t>(kFrames) * kDftCols;
-    d.tile_n = 128;
+    d.tile_n = 256;
     const int rc = wfl_gemm(&d, stream_);
     if (rc != WFL_OK) return rc;
   }
