@@ -137,27 +137,26 @@ lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B,
   }
   cluster_sync_all();  // every CTA of the cluster is running and initialised before any DSMEM traffic
 
-  // cells (unit, batch b0 + 8 nt + 2q) and (.. + 2q + 1) per column tile nt; used by khalf==0 warps
-  float c_state[kNT][2];
-  int bq[kNT][2];
+  // One cell per thread and column tile: the two K-half warps of a unit group split the two batch columns of an MMA
+  // accumulator pair between them (khalf 0 -> batch b0 + 8 nt + 2q, khalf 1 -> .. + 2q + 1), so the gate math --
+  // the longest part of a step -- runs on all warps instead of on half of them.
+  float c_state[kNT];
+  int bq[kNT];
 #pragma unroll
   for (int nt = 0; nt < kNT; ++nt) {
-    c_state[nt][0] = c_state[nt][1] = 0.f;
-    bq[nt][0] = b0 + nt * 8 + 2 * q;
-    bq[nt][1] = bq[nt][0] + 1;
+    c_state[nt] = 0.f;
+    bq[nt] = b0 + nt * 8 + 2 * q + khalf;
   }
   const int64_t row_stride = static_cast<int64_t>(8) * H;  // gx row: [dir][unit][gate]
   const float4* gx_base = reinterpret_cast<const float4*>(gx) + (static_cast<int64_t>(dir) * H + unit);
   auto gx_ptr = [&](int b, int t) { return gx_base + (static_cast<int64_t>(b) * T + t) * (row_stride / 4); };
-  float4 pre[kNT][2];
-#pragma unroll
-  for (int nt = 0; nt < kNT; ++nt) pre[nt][0] = pre[nt][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (khalf == 0) {
+  float4 pre[kNT];
+  {
     const int t_first = dir == 0 ? 0 : T - 1;
 #pragma unroll
     for (int nt = 0; nt < kNT; ++nt) {
-      if (bq[nt][0] < B) pre[nt][0] = __ldg(gx_ptr(bq[nt][0], t_first));
-      if (bq[nt][1] < B) pre[nt][1] = __ldg(gx_ptr(bq[nt][1], t_first));
+      pre[nt] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bq[nt] < B) pre[nt] = __ldg(gx_ptr(bq[nt], t_first));
     }
   }
   const uint32_t hbuf_local = smem_u32(hbuf_raw);
@@ -201,54 +200,45 @@ lstm_kernel(const float* __restrict__ gx, const __half* __restrict__ whh, int B,
         acc_if[nt][0][i] += acc_if[nt][1][i];
         acc_go[nt][0][i] += acc_go[nt][1][i];
       }
-    if (khalf == 1) {
+    // each K-half warp hands the partial sums of the OTHER warp's batch column to it: {i, f, g, o} of one column
+    // (accumulator layout: [0],[1] = first gate of the tile (rows g) for batch 2q, 2q+1; [2],[3] = second gate (rows g+8))
+    const int oc = khalf ^ 1;  // the column this thread gives away
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        float4* pp = reinterpret_cast<float4*>(part + ((group * kNT + nt) * 32 + lane) * 8);
-        pp[0] = make_float4(acc_if[nt][0][0], acc_if[nt][0][1], acc_if[nt][0][2], acc_if[nt][0][3]);
-        pp[1] = make_float4(acc_go[nt][0][0], acc_go[nt][0][1], acc_go[nt][0][2], acc_go[nt][0][3]);
-      }
+    for (int nt = 0; nt < kNT; ++nt) {
+      float4* pp = reinterpret_cast<float4*>(part + (((group * kNT + nt) * 2 + oc) * 32 + lane) * 4);
+      // (selects, not runtime indices: the accumulators must stay in registers)
+      *pp = oc ? make_float4(acc_if[nt][0][1], acc_if[nt][0][3], acc_go[nt][0][1], acc_go[nt][0][3])
+               : make_float4(acc_if[nt][0][0], acc_if[nt][0][2], acc_go[nt][0][0], acc_go[nt][0][2]);
     }
     __syncthreads();
-    if (khalf == 0) {
+    {
       // this step's input pre-activations were requested one step ago; take them, then immediately request the next
       // step's.  (Nothing may read pre[] again before the next iteration: a register copy of the in-flight load at
       // the end of this block stalled ~1100 cycles per step on the scoreboard -- per-phase clock64 trace, profiles/.)
-      float4 in[kNT][2];
+      float4 in[kNT];
 #pragma unroll
-      for (int nt = 0; nt < kNT; ++nt) {
-        in[nt][0] = pre[nt][0];
-        in[nt][1] = pre[nt][1];
-      }
+      for (int nt = 0; nt < kNT; ++nt) in[nt] = pre[nt];
       if (s + 1 < T) {
         const int tn = dir == 0 ? s + 1 : T - 2 - s;
 #pragma unroll
-        for (int nt = 0; nt < kNT; ++nt) {
-          if (bq[nt][0] < B) pre[nt][0] = __ldg(gx_ptr(bq[nt][0], tn));
-          if (bq[nt][1] < B) pre[nt][1] = __ldg(gx_ptr(bq[nt][1], tn));
-        }
+        for (int nt = 0; nt < kNT; ++nt)
+          if (bq[nt] < B) pre[nt] = __ldg(gx_ptr(bq[nt], tn));
       }
       const int ul = group * 8 + g;  // unit inside this CTA's slice
 #pragma unroll
       for (int nt = 0; nt < kNT; ++nt) {
-        const float4* pp = reinterpret_cast<const float4*>(part + ((group * kNT + nt) * 32 + lane) * 8);
-        const float4 p_if = pp[0], p_go = pp[1];
-        const float4 in0 = in[nt][0], in1 = in[nt][1];
-        // accumulator layout: [0],[1] = first gate of the tile (rows g) for batch 2q, 2q+1; [2],[3] = second gate (rows g+8)
-        const float ai0 = acc_if[nt][0][0] + p_if.x + in0.x, ai1 = acc_if[nt][0][1] + p_if.y + in1.x;
-        const float af0 = acc_if[nt][0][2] + p_if.z + in0.y, af1 = acc_if[nt][0][3] + p_if.w + in1.y;
-        const float ag0 = acc_go[nt][0][0] + p_go.x + in0.z, ag1 = acc_go[nt][0][1] + p_go.y + in1.z;
-        const float ao0 = acc_go[nt][0][2] + p_go.z + in0.w, ao1 = acc_go[nt][0][3] + p_go.w + in1.w;
-        c_state[nt][0] = sigmoid_acc(af0) * c_state[nt][0] + sigmoid_acc(ai0) * tanh_acc(ag0);
-        c_state[nt][1] = sigmoid_acc(af1) * c_state[nt][1] + sigmoid_acc(ai1) * tanh_acc(ag1);
-        const float h0 = sigmoid_acc(ao0) * tanh_acc(c_state[nt][0]);
-        const float h1 = sigmoid_acc(ao1) * tanh_acc(c_state[nt][1]);
-        stage[(nt * 8 + 2 * q) * Cfg::kUnits + ul] = to_f16(h0);
-        stage[(nt * 8 + 2 * q + 1) * Cfg::kUnits + ul] = to_f16(h1);
-        if (y_f32 != nullptr) {
-          if (bq[nt][0] < B) y_f32[(static_cast<int64_t>(bq[nt][0]) * T + t) * (2 * H) + dir * H + unit] = h0;
-          if (bq[nt][1] < B) y_f32[(static_cast<int64_t>(bq[nt][1]) * T + t) * (2 * H) + dir * H + unit] = h1;
-        }
+        const float4 pp = *reinterpret_cast<const float4*>(part + (((group * kNT + nt) * 2 + khalf) * 32 + lane) * 4);
+        // (khalf-0 partial) + (khalf-1 partial) + input, in that order for both columns
+        const float mi = khalf ? acc_if[nt][0][1] : acc_if[nt][0][0], mf = khalf ? acc_if[nt][0][3] : acc_if[nt][0][2];
+        const float mg = khalf ? acc_go[nt][0][1] : acc_go[nt][0][0], mo = khalf ? acc_go[nt][0][3] : acc_go[nt][0][2];
+        const float ai = (khalf == 0 ? mi + pp.x : pp.x + mi) + in[nt].x;
+        const float af = (khalf == 0 ? mf + pp.y : pp.y + mf) + in[nt].y;
+        const float ag = (khalf == 0 ? mg + pp.z : pp.z + mg) + in[nt].z;
+        const float ao = (khalf == 0 ? mo + pp.w : pp.w + mo) + in[nt].w;
+        c_state[nt] = sigmoid_acc(af) * c_state[nt] + sigmoid_acc(ai) * tanh_acc(ag);
+        const float hv = sigmoid_acc(ao) * tanh_acc(c_state[nt]);
+        stage[(nt * 8 + 2 * q + khalf) * Cfg::kUnits + ul] = to_f16(hv);
+        if (y_f32 != nullptr && bq[nt] < B) y_f32[(static_cast<int64_t>(bq[nt]) * T + t) * (2 * H) + dir * H + unit] = hv;
       }
     }
     __syncthreads();
