@@ -188,7 +188,7 @@ def _attn_ref(qkv, B, T, H, hd, scale, bias=None):
 
 @pytest.mark.parametrize("hd,H,T,B", [(64, 2, 128, 1), (64, 3, 300, 2), (64, 8, 1500, 1), (256, 2, 200, 2),
                                        (256, 2, 1500, 1), (384, 2, 333, 1), (512, 2, 300, 2), (640, 2, 457, 1),
-                                       (512, 2, 1499, 1)])
+                                       (512, 2, 1499, 1), (64, 2, 1, 2), (64, 1, 65, 1), (256, 2, 63, 1), (64, 4, 129, 3)])
 def test_attention(hd, H, T, B):
     d = H * hd
     qkv = _rand(B, T, 3 * d, seed=23).half()
@@ -437,7 +437,8 @@ def test_merge_rejects_bad_mode():
 
 # ----------------------------------------------------------------------------------------- BiLSTM
 @pytest.mark.parametrize("H,B,T", [(256, 3, 50), (384, 9, 37), (192, 8, 120), (512, 8, 30), (640, 5, 25),
-                                   (384, 64, 12), (256, 70, 9)])  # the last two: 16 batch items per cluster
+                                   (384, 64, 12), (256, 70, 9),  # 16 batch items per cluster
+                                   (384, 3, 1), (256, 9, 2), (192, 1, 3)])  # shortest sequences: h exchange start-up
 def test_lstm_layer(H, B, T):
     """One bidirectional layer vs the step-by-step oracle restatement of nn.LSTM (REF/model.py:105-111)."""
     d = 2 * H
