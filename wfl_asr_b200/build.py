@@ -40,6 +40,16 @@ def build(force=False, verbose=False):
     digest = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB_PATH
+    # one builder at a time (the ranks of a multi-GPU launch all import the package at once)
+    import fcntl
+    with open(os.path.join(PKG_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+            return LIB_PATH
+        return _build_locked(digest, verbose)
+
+
+def _build_locked(digest, verbose):
     objs = []
     build_dir = os.path.join(PKG_DIR, "build")
     os.makedirs(build_dir, exist_ok=True)
