@@ -88,8 +88,7 @@ class Engine:
                               sd[f"dilated_conv_stack.{2 * i}.bias"])
         # classifier in split precision: A = [hi | lo], W = [hi | hi | lo]  (x_hi w_hi + x_lo w_hi + x_hi w_lo)
         wc = packing.pad_rows(sd["classifier.weight"].float(), self.Lp)
-        self._put("cls.w", packing.split_hi_lo(wc))  # already f16
-        self.W["cls.w"] = packing.split_hi_lo(wc.to(self.dev))
+        self.W["cls.w"] = packing.split_hi_lo(wc.to(self.dev))  # f16 [Lp, 3d]
         bc = torch.zeros(self.Lp, device=self.dev)
         bc[:self.L] = sd["classifier.bias"].float().to(self.dev)
         self.W["cls.b"] = bc
