@@ -101,7 +101,7 @@ def wavlm_conv0(wave, n_samples, w, gamma, beta, norm_mode, out, out_batch_strid
     rc = _lib.load().wfl_wavlm_conv0(_ptr(wave), wave.stride(0), n_samples, wave.shape[0], _ptr(w), _ptr(gamma),
                                      _ptr(beta), norm_mode, _ptr(out), out_batch_stride, _ptr(scratch), _stream())
     _lib.check(rc, "wfl_wavlm_conv0")
-    _count(2)
+    _count(3)  # statistics partials, ordered finish, conv + norm + GELU
 
 
 def wavlm_gate(x_f16, row_stride, B, T, H, hd, gw, gb, gconst, gate):
@@ -162,7 +162,7 @@ def whisper_logmel(wave, n_samples, basis_split, filters, n_mels, out, scratch):
                                         _ptr(out), out.shape[-1], _ptr(planes), _ptr(dft), _ptr(logspec), _ptr(smax),
                                         _stream())
     _lib.check(rc, "wfl_whisper_logmel")
-    _count(4)
+    _count(5)  # prep, DFT GEMM, filter spans, power + mel + log, normalise
 
 
 def decode_frames(logits2d, L, o_id, threshold, ids):
