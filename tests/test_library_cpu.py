@@ -28,6 +28,31 @@ def test_library_exports_header_symbols():
     assert lib.wfl_abi_version() == 1
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _lib.py must have the C compiler's layout of include/wfl_b200.h (size and the offsets of
+    the fields a mismatch would silently corrupt), and the header's constants must equal the Python ones."""
+    import ctypes
+    import shutil
+    import subprocess
+    from wfl_asr_b200 import _lib, ops
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "wfl_b200.h"\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(wfl_gemm_desc), offsetof(wfl_gemm_desc, w), '
+        'offsetof(wfl_gemm_desc, bias), offsetof(wfl_gemm_desc, out), offsetof(wfl_gemm_desc, tile_n), '
+        'offsetof(wfl_gemm_desc, out_col_group_stride), sizeof(wfl_segment), (int)WFL_MAX_SLABS, (int)WFL_WAVLM_STATS_DOUBLES); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    G = _lib.GemmDesc
+    want = [ctypes.sizeof(G), G.w.offset, G.bias.offset, G.out.offset, G.tile_n.offset, G.out_col_group_stride.offset,
+            ctypes.sizeof(_lib.Segment), _lib.WFL_MAX_SLABS, ops.WAVLM_STATS_DOUBLES]
+    assert got == want, (got, want)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_compute_fails_loudly_without_gpu():
     from wfl_asr_b200 import ops
