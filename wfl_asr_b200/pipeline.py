@@ -117,11 +117,15 @@ class Labeler:
         Launches: decode_frames, median_filter (if size > 1), bio_decode, merge_segments."""
         B, T, L = logits.shape
         ws = self._buffers(B, T)
-        if lengths is None:
-            lengths = torch.full((B,), T, dtype=torch.int32, device=self.dev)
+        if lengths is None:  # full-length clips, one file per clip: constant index vectors, built once per shape
+            lengths = ws.get("full_lengths")
+            if lengths is None:
+                lengths = ws["full_lengths"] = torch.full((B,), T, dtype=torch.int32, device=self.dev)
         n_files = B if file_clip_begin is None else file_clip_begin.numel() - 1
         if file_clip_begin is None:
-            file_clip_begin = torch.arange(B + 1, dtype=torch.int32, device=self.dev)
+            file_clip_begin = ws.get("one_clip_per_file")
+            if file_clip_begin is None:
+                file_clip_begin = ws["one_clip_per_file"] = torch.arange(B + 1, dtype=torch.int32, device=self.dev)
         lg2 = logits.reshape(B * T, L) if logits.is_contiguous() else logits.as_strided((B * T, L), (logits.stride(1), 1))
         ops.decode_frames(lg2, L, self.o_id, self.threshold, ws["ids"])
         ids = ws["ids"]
