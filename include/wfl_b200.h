@@ -136,6 +136,12 @@ int wfl_split_f16(const float* x, int64_t rows, int32_t d, void* out_hi_lo, void
  * epilogue accumulates into it; TF/models/whisper/modeling_whisper.py:622-625). */
 int wfl_broadcast_rows(const float* src, int64_t rows, int32_t d, int32_t batches, float* dst, void* stream);
 
+/* out[r][g*w_out + j] = in[r][g*w_in + j] for g < groups, j < w_out (fp32; widths multiples of 4): removes the
+ * zero-padded units per direction after wfl_lstm_layer ran at a padded hidden size (nn.LSTM hidden sizes the
+ * recurrence is not built for, e.g. 40 when encoder_type is "none", REF/model.py:82-91,105-111). */
+int wfl_gather_cols(const float* in, int64_t rows, int32_t groups, int32_t w_in, int32_t w_out, float* out,
+                    void* stream);
+
 /* out[r][j] = sigmoid(dot(x[r], w[j]) + b[j]), j < n_out <= 4: the 1x1 conv + Sigmoid that ends the
  * boundary-offset head (REF/model.py:140-141,193).  x f16 [rows][d], w fp32 [n_out][d]. */
 int wfl_rowdot_sigmoid(const void* x_f16, int64_t rows, int32_t d, const float* w, const float* b, int32_t n_out,
@@ -183,6 +189,18 @@ int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_t n_samples
                        const void* basis_split_f16, const float* mel_filters, int32_t n_mels, void* out_f16,
                        int32_t out_stride, void* scratch_planes, float* scratch_dft, float* scratch_logspec,
                        float* scratch_max, void* stream);
+
+/* ---- encoder_type "none": MelSpectrogram power features (REF/model.py:82-91,149-150 ->
+ * torchaudio.transforms.MelSpectrogram(n_fft 400, hop, power 2, center, reflect) then transpose(1, 2)) --
+ * out fp32 [B][frames][out_stride], frames = 1 + n_samples / hop, columns [0, n_mels) written.  The clip itself
+ * (n_samples > 200) is reflect-padded; same split-precision tensor-core DFT as wfl_whisper_logmel with
+ * basis_split_f16 built from the module's window buffer; mel_filters fp32 [201][n_mels] is its fb buffer.
+ * scratch_planes: f16 2*plane*B + 4096 elements, plane = (frames - 1 + ceil(400 / hop)) * hop;
+ * scratch_dft: fp32 [B][frames][448]; scratch_span: 256 floats.  n_mels: multiple of 16, <= 128; hop: multiple of 8.
+ */
+int wfl_mel_power(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, int32_t hop,
+                  const void* basis_split_f16, const float* mel_filters, int32_t n_mels, float* out,
+                  int32_t out_stride, void* scratch_planes, float* scratch_dft, float* scratch_span, void* stream);
 
 /* ---- K15/K18/K19: decode -> median -> BIO -> merge --------------------------------------------- */
 typedef struct wfl_segment {

@@ -46,9 +46,14 @@ def encoder_arch(config):
         a = dict(WHISPER_ARCH[m["whisper_model"].split("whisper-")[-1]])
     elif et == "wavlm":
         a = dict(WAVLM_ARCH[m["wavlm_model"].split("wavlm-")[-1]])
+    elif et in ("none", "null"):  # REF/model.py:82-91: no encoder, MelSpectrogram power features are the hidden states
+        data = config["data"]
+        a = dict(d=data.get("n_mels", 80), mels=data.get("n_mels", 80), layers=0,
+                 hop=int(data.get("frame_duration", 0.02) * data["sample_rate"]), sample_rate=data["sample_rate"])
+        et = "none"
     else:
         raise ValueError("Unsupported encoder type. Use 'whisper', 'wavlm', or 'none'.")
-    if "encoder_layers_override" in m:  # test hook: shallower encoder, same layer maths
+    if "encoder_layers_override" in m and et != "none":  # test hook: shallower encoder, same layer maths
         a["layers"] = m["encoder_layers_override"]
     a["type"] = et
     return a
@@ -105,6 +110,32 @@ def whisper_log_mel(wave, n_mels):
     mx = log_spec.amax(dim=(1, 2), keepdim=True)
     log_spec = torch.maximum(log_spec, mx - 8.0)
     return (log_spec + 4.0) / 4.0
+
+
+def htk_mel_filters(n_mels, n_freqs=201, sr=16000, f_min=0.0, f_max=None):
+    """torchaudio.functional.melscale_fbanks(norm=None, mel_scale="htk") in its fp32 arithmetic: the value of the
+    ``mel_extractor.mel_scale.fb`` buffer [n_freqs, n_mels] that REF/model.py:85-90 registers (f_max = sr/2)."""
+    f_max = float(sr // 2) if f_max is None else f_max
+    all_freqs = torch.linspace(0, sr // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + f_min / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+def mel_power(wave, window, fb, hop):
+    """torchaudio.transforms.MelSpectrogram as configured at REF/model.py:85-90, then REF/model.py:150's transpose:
+    torch.stft(n_fft = win = len(window), hop, center, reflect, onesided) -> |.|^2 -> fb^T.  [B, N] -> [B, 1 + N//hop, n_mels]."""
+    n_fft = window.numel()
+    spec = torch.stft(wave.float(), n_fft, hop, n_fft, window=window, center=True, pad_mode="reflect",
+                      normalized=False, onesided=True, return_complex=True)
+    power = spec.abs().pow(2.0)  # [B, n_fft/2+1, T]
+    return torch.matmul(power.transpose(-1, -2), fb)
 
 
 def whisper_sinusoids(length, channels, max_timescale=10000.0):
@@ -299,6 +330,8 @@ def encode(wave, sd, config):
     arch = encoder_arch(config)
     if arch["type"] == "whisper":
         return whisper_encoder(whisper_log_mel(wave, arch["mels"]), sd, arch)
+    if arch["type"] == "none":  # REF/model.py:149-150
+        return mel_power(wave, sd["mel_extractor.spectrogram.window"], sd["mel_extractor.mel_scale.fb"], arch["hop"])
     return wavlm_encoder(wave, sd, arch)
 
 
@@ -404,6 +437,9 @@ def random_state_dict(config, n_labels, seed=0):
             lin(p + "fc2", d, arch["ffn"])
             ln(p + "final_layer_norm", d)
         ln("encoder.layer_norm", d)
+    elif arch["type"] == "none":  # buffers of torchaudio's MelSpectrogram (REF/model.py:85-90), not random
+        sd["mel_extractor.spectrogram.window"] = torch.hann_window(400)
+        sd["mel_extractor.mel_scale.fb"] = htk_mel_filters(arch["mels"], 201, arch["sample_rate"])
     else:
         C = WAVLM_CONV["dim"]
         for i, k in enumerate(WAVLM_CONV["kernels"]):

@@ -4,7 +4,8 @@
 audio.  Only reference OUTPUTS are committed (frame-strided logits/offsets + all argmax ids); the
 weights are regenerated from the seed on whatever box runs the tests.
 
-Run:  python tests/golden/make_forward_golden.py     (needs /root/reference)
+Run:  python tests/golden/make_forward_golden.py [case ...]    (needs /root/reference; with case names only those
+      entries of the existing file are replaced)
 """
 import copy
 import os
@@ -38,6 +39,8 @@ CASES = {
     # conformer_heads=4 -> head_dim 256 (heads=2 at d=1024 needs the head_dim-512 attention variant, not built yet)
     "wavlm_large": (dict(encoder_type="wavlm", wavlm_model="microsoft/wavlm-large", num_conformer_layers=1,
                          conformer_heads=4, enable_bilstm=False), 2, 2, 1.5, 14),
+    # encoder_type "none" (REF/model.py:82-91): MelSpectrogram power features, hidden size 80, 101 frames per 2 s
+    "mel_none_full": (dict(encoder_type="none"), 0, 2, 2.0, 15),
 }
 
 
@@ -59,8 +62,10 @@ def case_inputs(name):
 
 
 def main():
-    out = {}
-    for name in CASES:
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "forward_golden.npz")
+    only = sys.argv[1:]
+    out = dict(np.load(dst)) if only else {}
+    for name in (only or CASES):
         cfg, labels, sd, wave, lang = case_inputs(name)
         ref = ref_loader.build_reference_model(cfg, labels, layer_override=cfg["model"]["encoder_layers_override"],
                                                randomize_bn=False)
@@ -71,7 +76,6 @@ def main():
         out[name + "/offsets"] = offsets[:, ::STRIDE].numpy()
         out[name + "/argmax"] = logits.argmax(-1).numpy().astype(np.int16)
         print(name, tuple(logits.shape), float(logits.abs().max()))
-    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "forward_golden.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst) // 1024, "KiB")
 

@@ -76,8 +76,10 @@ def test_state_dict_matches_reference_layout():
         assert set(own) == set(sd), (name, sorted(set(own) ^ set(sd))[:6])
         for k in sd:
             assert own[k].shape == sd[k].shape and own[k].dtype == sd[k].dtype, (name, k)
+            if k.startswith("mel_extractor."):  # buffers, not weights: the holder's defaults are torchaudio's values
+                assert torch.equal(own[k], sd[k]), (name, k)
         model.load_state_dict(sd, strict=True)
-        assert model.label2id["O"] == labels.index("O") and model.encoder_type in ("whisper", "wavlm")
+        assert model.label2id["O"] == labels.index("O") and model.encoder_type in ("whisper", "wavlm", "none")
 
 
 def test_model_rejects_bad_encoder_type():

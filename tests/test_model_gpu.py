@@ -79,7 +79,7 @@ def test_lang_none_skips_projection():
     assert rel <= 2e-3 and agree_safe == 1.0
 
 
-@pytest.mark.parametrize("name", [n for n in ("whisper_base_full", "wavlm_base_plus") if n in SUPPORTED])
+@pytest.mark.parametrize("name", [n for n in ("whisper_base_full", "wavlm_base_plus", "mel_none_full") if n in SUPPORTED])
 def test_language_mean_fast_path(name):
     """REF/infer.py:265-276 (no --lang-id): mean over per-language forwards.  The fast path runs the encoder once and
     must equal the per-language full forwards bit for bit, and the fp32 oracle's mean within the logit tolerance."""
@@ -236,7 +236,7 @@ def test_infer_audio_end_to_end(tmp_path, seconds, file_sr):
     assert n_agree / n_frames >= 0.995
 
 
-@pytest.mark.parametrize("name", ["whisper_base_cfg2", "wavlm_base_plus"])
+@pytest.mark.parametrize("name", ["whisper_base_cfg2", "wavlm_base_plus", "mel_none_full"])
 def test_infer_folder_batched_equals_per_file(tmp_path, name, capsys):
     """infer_folder labels the folder in shared batches; every .lab must equal what infer_audio writes for the same
     file alone (long file -> 30 s chunks, 44.1 kHz file -> resampled, forced phoneme list -> aligned), for the
@@ -272,7 +272,8 @@ def test_infer_folder_batched_equals_per_file(tmp_path, name, capsys):
     capsys.readouterr()
 
 
-@pytest.mark.parametrize("name,bucket", [("wavlm_base_plus", 8000), ("wavlm_base_plus", 1), ("whisper_base_cfg2", 8000)])
+@pytest.mark.parametrize("name,bucket", [("wavlm_base_plus", 8000), ("wavlm_base_plus", 1), ("whisper_base_cfg2", 8000),
+                                         ("mel_none_full", 8000)])
 def test_bulk_label_corpus_ragged(name, bucket):
     """bulk.label_corpus (BASELINE configs[3]: utterances of different lengths, length-bucketed): per bucket batch the
     logits match the fp32 oracle on the same zero-padded batch (the reference's batched caller pads without masks,

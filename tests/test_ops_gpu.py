@@ -165,6 +165,46 @@ def test_gemm_batched_bias_and_split_precision():
     _report("split3", out, ref, 2e-4)
 
 
+@pytest.mark.parametrize("mode", ["f16", "add_f32", "glu"])
+def test_gemm_width_not_a_multiple_of_64(mode):
+    """Hidden size 80 (encoder_type "none"): A rows are 80 wide, the K slab is 128 with zero weights behind column 80
+    and the tensor map zero-fills the columns past a_cols even when the MEMORY behind them holds other data (here
+    NaN-free garbage: the next row); n = 80 output columns with a 128-wide tile; 3 shifted slabs (conv k3)."""
+    B, T, d, dk = 3, 201, 80, 128
+    a = _rand(B, T, d, seed=61).half()
+    w = _rand(d if mode != "glu" else 2 * dk, 3, d, scale=(3 * d) ** -0.5, seed=62)
+    if mode == "glu":  # value rows 0..79 and gate rows 128..207 are real, the rest zero (as engine.py packs pw1)
+        w[80:128] = 0
+        w[208:] = 0
+    wp = torch.zeros(w.shape[0], 3, dk, device=DEV)
+    wp[:, :, :d] = w
+    wp = wp.reshape(w.shape[0], 3 * dk).half()
+    bias = _rand(w.shape[0], seed=63)
+    if mode == "glu":
+        bias[80:128] = 0
+        bias[208:] = 0
+    x = F.pad(a.float(), (0, 0, 1, 1))
+    cols = torch.cat([x[:, j:j + T] for j in range(3)], dim=-1)  # [B, T, 3*d] tap-major
+    acc = cols @ w.half().float().reshape(w.shape[0], 3 * d).T + bias
+    kw = dict(n=w.shape[0], slab_k=dk, shifts=[-1, 0, 1], cols=[0, 0, 0], a_rows=T, a_cols=d, a_row_stride=d,
+              a_batch_stride=T * d, batches=B, m_rows=T, bias=bias)
+    if mode == "f16":
+        out = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.float16)
+        ops.gemm(a, wp, out, out_row_stride=d, out_batch_stride=T * d, act=ops.ACT_GELU, **kw)
+        _report("ragged f16", out, F.gelu(acc), 1e-2)
+    elif mode == "add_f32":
+        base = _rand(B, T, d, seed=64)
+        out = base.clone()
+        ops.gemm(a, wp, out, out_row_stride=d, out_batch_stride=T * d, out_mode=ops.OUT_ADD_F32, alpha=0.5, **kw)
+        _report("ragged add", out, base + 0.5 * acc, 2e-3)
+    else:
+        out = torch.full((B, T, dk), float("nan"), device=DEV, dtype=torch.float16)
+        ops.gemm(a, wp, out, out_row_stride=dk, out_batch_stride=T * dk, out_mode=ops.OUT_GLU_F16, tile_n=256, **kw)
+        ref = acc[..., :dk] * torch.sigmoid(acc[..., dk:])
+        _report("ragged glu", out, ref, 1e-2)
+        assert not out[..., d:].any()  # padded channels come out as exact zeros
+
+
 def test_gemm_rejects_bad_arguments():
     a = torch.zeros(128, 100, device=DEV, dtype=torch.float16)
     w = torch.zeros(64, 100, device=DEV, dtype=torch.float16)
@@ -328,6 +368,48 @@ def test_whisper_logmel(n_mels):
     mx = lo.amax(dim=(1, 2), keepdim=True)
     renorm = (torch.maximum(lo, mx - 8.0) + 4.0) / 4.0
     assert (renorm - ref).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("n_mels,hop,lens", [(80, 320, (32000, 32123)), (64, 160, (4001,)), (128, 320, (201, 480000))])
+def test_mel_power_matches_oracle(n_mels, hop, lens):
+    """encoder_type "none" front-end (REF/model.py:85-90,150): MelSpectrogram power vs torch.stft in fp32.  Any clip
+    length (frames = 1 + n // hop), the clip's own reflect padding, HTK filters and window taken from the module's
+    buffers.  Tolerance: 2e-5 of each clip's largest value + 1e-6 relative (split-precision DFT, fp32 power/mel)."""
+    from wfl_asr_b200.frontend import dft_basis_split
+    window = torch.hann_window(400)
+    fb = to.htk_mel_filters(n_mels)
+    basis = dft_basis_split(window.double().numpy()).to(DEV)
+    for n in lens:
+        B = 2
+        wave = torch.stack([torch.from_numpy(to.synth_wave(70 + i, n / 16000.0)).float()[:n] for i in range(B)])
+        assert wave.shape[1] == n
+        T = ops.mel_power_frames(n, hop)
+        out = torch.full((B, T, n_mels + 8), float("nan"), device=DEV)
+        ops.mel_power(wave.to(DEV), n, hop, basis, fb.to(DEV), n_mels, out, ops.mel_power_scratch(B, n, hop, DEV))
+        ref = to.mel_power(wave, window, fb, hop)
+        assert ref.shape == (B, T, n_mels)
+        got = out[..., :n_mels].cpu()
+        assert torch.isnan(out[..., n_mels:]).all()  # columns past n_mels are not touched
+        tol = 2e-5 * ref.amax(dim=(1, 2), keepdim=True) + 1e-6 * ref
+        bad = ((got - ref).abs() > tol)
+        assert not bad.any(), (n, int(bad.sum()), float((got - ref).abs().max()), float(ref.max()))
+
+
+def test_mel_power_rejects_short_clip():
+    from wfl_asr_b200.frontend import dft_basis_split
+    basis = dft_basis_split().to(DEV)
+    fb = to.htk_mel_filters(80).to(DEV)
+    wave = torch.zeros(1, 200, device=DEV)
+    out = torch.empty(1, 1, 80, device=DEV)
+    with pytest.raises(ops.WflError):  # torch.stft refuses reflect padding >= the clip length as well
+        ops.mel_power(wave, 200, 320, basis, fb, 80, out, ops.mel_power_scratch(1, 200, 320, DEV))
+
+
+def test_gather_cols():
+    src = _rand(1000, 2 * 192, seed=5)
+    dst = torch.full((1000, 80), float("nan"), device=DEV)
+    ops.gather_cols(src, dst, 2, 192, 40)
+    assert torch.equal(dst, src.view(1000, 2, 192)[:, :, :40].reshape(1000, 80))
 
 
 # ----------------------------------------------------------------------------------------- post-processing

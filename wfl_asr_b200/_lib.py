@@ -53,6 +53,8 @@ SIGNATURES = {
     "wfl_layernorm": [_P, _I64, _I32, _P, _P, _P, _P, _F, _P, _P, _I32, _P],
     "wfl_split_f16": [_P, _I64, _I32, _P, _P],
     "wfl_broadcast_rows": [_P, _I64, _I32, _I32, _P, _P],
+    "wfl_gather_cols": [_P, _I64, _I32, _I32, _I32, _P, _P],
+    "wfl_mel_power": [_P, _I64, _I32, _I32, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P, _P],
     "wfl_rowdot_sigmoid": [_P, _I64, _I32, _P, _P, _I32, _P, _P],
     "wfl_peak_normalize": [_P, _P, _I32, _P, _I64, _P, _P, _P],
     "wfl_resample_sinc": [_P, _I64, _I32, _I32, _I32, _P, _P, _I64, _P],

@@ -1,5 +1,5 @@
 """Architecture tables for the encoders the reference instantiates by name
-(REF/model.py:57-80: ``whisper_model`` / ``wavlm_model``).  Values are the public model-card
+(REF/model.py:57-91: ``whisper_model`` / ``wavlm_model`` / encoder_type "none").  Values are the public model-card
 hyper-parameters; they cannot be fetched offline, so ``config["model"]`` may
 override any of them through ``encoder_arch_override`` (a dict) and the test-only
 ``encoder_layers_override``."""
@@ -34,6 +34,13 @@ def encoder_arch(config):
     elif et == "wavlm":
         name = m["wavlm_model"].split("wavlm-")[-1]
         table = WAVLM
+    elif et in ("none", "null"):
+        # REF/model.py:82-91: no encoder; torchaudio MelSpectrogram(n_fft 400, hop = frame_duration * sample_rate) power
+        # features ARE the hidden states, so the hidden size is n_mels
+        data = config["data"]
+        n_mels = int(data.get("n_mels", 80))
+        return dict(type="none", d=n_mels, mels=n_mels, layers=0, sample_rate=int(data["sample_rate"]),
+                    hop=int(data.get("frame_duration", 0.02) * data["sample_rate"]))
     else:
         raise ValueError("Unsupported encoder type. Use 'whisper', 'wavlm', or 'none'.")  # REF/model.py:94
     if name not in table:

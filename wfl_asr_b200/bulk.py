@@ -55,7 +55,7 @@ def label_corpus(model, waves, lang_ids=None, *, median_filter=1, merge_mode="ri
         logits, offsets = model(wave, lang)
         T = logits.shape[1]
         # like the reference's batched caller (REF/train.py:485-495): decode each item on its own frame count
-        valid = torch.tensor([min(T, shard.frames_for(lens[i], etype)) for i in group],
+        valid = torch.tensor([min(T, shard.frames_for(lens[i], etype, model.arch.get("hop", 320))) for i in group],
                              dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
         _, merged, nout, fcb, n_files = labeler.postprocess(logits, offsets, valid)
         # results leave through pinned buffers; the host decodes batch k-1 while batch k runs on the GPU

@@ -76,9 +76,13 @@ __global__ void mel_span_kernel(const float* __restrict__ filt, int n_mels, int2
   span[m] = hi < 0 ? make_int2(0, 0) : make_int2(lo, hi - lo + 1);
 }
 
+// kPower: write the mel power itself (fp32 rows of out_stride floats) -- the MelSpectrogram front-end of
+// encoder_type "none" (REF/model.py:85-90,150) -- instead of log10 + the running clip maximum.
+template <bool kPower>
 __global__ void __launch_bounds__(256, 2)
-logmel_post_kernel(const float* __restrict__ dft /*[B][3000][448]*/, const float* __restrict__ filt, int n_mels,
-                   const int2* __restrict__ span, float* __restrict__ logspec, unsigned* __restrict__ clip_max_key) {
+logmel_post_kernel(const float* __restrict__ dft /*[B][frames][448]*/, int frames, const float* __restrict__ filt,
+                   int n_mels, const int2* __restrict__ span, float* __restrict__ logspec, int out_stride,
+                   unsigned* __restrict__ clip_max_key) {
   extern __shared__ float pw[];  // [kFrameTile][kPwStride]
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFrameTile;
@@ -88,8 +92,8 @@ logmel_post_kernel(const float* __restrict__ dft /*[B][3000][448]*/, const float
     const int f = i / kBins, k = i - f * kBins;
     const int t = t0 + f;
     float v = 0.f;
-    if (t < kFrames) {
-      const float2 c = *reinterpret_cast<const float2*>(dft + (static_cast<int64_t>(b) * kFrames + t) * kDftCols + 2 * k);
+    if (t < frames) {
+      const float2 c = *reinterpret_cast<const float2*>(dft + (static_cast<int64_t>(b) * frames + t) * kDftCols + 2 * k);
       v = c.x * c.x + c.y * c.y;
     }
     pw[f * kPwStride + k] = v;
@@ -114,15 +118,45 @@ logmel_post_kernel(const float* __restrict__ dft /*[B][3000][448]*/, const float
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
       const int t = t0 + 4 * fg + f;
-      if (t < kFrames) {
-        const float y = log10f(fmaxf(m[f], 1e-10f));
-        logspec[(static_cast<int64_t>(b) * kFrames + t) * n_mels + mel] = y;
-        local_max = fmaxf(local_max, y);
+      if (t < frames) {
+        if constexpr (kPower) {
+          logspec[(static_cast<int64_t>(b) * frames + t) * out_stride + mel] = m[f];
+        } else {
+          const float y = log10f(fmaxf(m[f], 1e-10f));
+          logspec[(static_cast<int64_t>(b) * frames + t) * out_stride + mel] = y;
+          local_max = fmaxf(local_max, y);
+        }
       }
     }
   }
-  local_max = warp_max(local_max);
-  if ((tid & 31) == 0 && local_max > -INFINITY) atomicMax(clip_max_key + b, float_order_key(local_max));
+  if constexpr (!kPower) {
+    local_max = warp_max(local_max);
+    if ((tid & 31) == 0 && local_max > -INFINITY) atomicMax(clip_max_key + b, float_order_key(local_max));
+  }
+}
+
+// General form of logmel_prep_kernel for the MelSpectrogram front-end: the clip itself (n_samples, not a 30 s
+// zero extension) is reflect-padded by n_fft/2 on both sides (torch.stft center=True), planes of plane_len samples.
+__global__ void __launch_bounds__(256) mel_prep_kernel(const float* __restrict__ wave, int64_t wave_stride,
+                                                       int n_samples, int64_t plane_len,
+                                                       __half* __restrict__ planes) {
+  const int b = blockIdx.y;
+  const float* w = wave + b * wave_stride;
+  __half* hi = planes + static_cast<int64_t>(b) * 2 * plane_len;
+  __half* mid = hi + plane_len;
+  for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < plane_len;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float x = 0.f;
+    if (i < n_samples + kNfft) {
+      int64_t j = i - kNfft / 2;
+      if (j < 0) j = -j;
+      if (j >= n_samples) j = 2 * (static_cast<int64_t>(n_samples) - 1) - j;
+      x = w[j];
+    }
+    const __half h = to_f16(x);
+    hi[i] = h;
+    mid[i] = to_f16(x - __half2float(h));
+  }
 }
 
 __global__ void __launch_bounds__(256) logmel_finish_kernel(const float* __restrict__ logspec,
@@ -165,7 +199,7 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
   if (B <= 0) return WFL_OK;
   static bool configured = false;
   if (!configured) {
-    WFL_CUDA(cudaFuncSetAttribute(logmel_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
+    WFL_CUDA(cudaFuncSetAttribute(logmel_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
     configured = true;
   }
   WFL_CUDA(cudaMemsetAsync(scratch_max, 0, sizeof(unsigned) * B, stream));
@@ -209,8 +243,9 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
     int2* span = reinterpret_cast<int2*>(scratch_max + ((B + 1) & ~1));
     mel_span_kernel<<<1, 128, 0, stream>>>(mel_filters, n_mels, span);
     WFL_CUDA(cudaGetLastError());
-    logmel_post_kernel<<<grid, 256, kPostSmem, stream>>>(scratch_dft, mel_filters, n_mels, span, scratch_logspec,
-                                                         reinterpret_cast<unsigned*>(scratch_max));
+    logmel_post_kernel<false><<<grid, 256, kPostSmem, stream>>>(scratch_dft, kFrames, mel_filters, n_mels, span,
+                                                                scratch_logspec, n_mels,
+                                                                reinterpret_cast<unsigned*>(scratch_max));
     WFL_CUDA(cudaGetLastError());
   }
   const int64_t rows = static_cast<int64_t>(B) * kFrames;
@@ -218,6 +253,75 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
   const unsigned g2 = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16));
   logmel_finish_kernel<<<g2, 256, 0, stream>>>(scratch_logspec, reinterpret_cast<const unsigned*>(scratch_max), n_mels,
                                                static_cast<__half*>(out_f16), out_stride, rows);
+  WFL_CUDA(cudaGetLastError());
+  return WFL_OK;
+}
+
+// encoder_type "none": torchaudio MelSpectrogram(n_fft 400, hop, power 2, center/reflect) + REF/model.py:150's transpose.
+// Same split-precision tensor-core DFT as above over the clip's own reflect padding; frames = 1 + n_samples / hop.
+extern "C" int wfl_mel_power(const float* wave, int64_t wave_stride, int32_t n_samples, int32_t B, int32_t hop,
+                             const void* basis_split_f16, const float* mel_filters, int32_t n_mels, float* out,
+                             int32_t out_stride, void* scratch_planes, float* scratch_dft, float* scratch_span,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  WFL_CHECK_ARG(wave && basis_split_f16 && mel_filters && out && scratch_planes && scratch_dft && scratch_span,
+                "wfl_mel_power: null pointer");
+  WFL_CHECK_ARG(n_mels >= 16 && n_mels <= 128 && n_mels % 16 == 0,
+                "wfl_mel_power: n_mels must be a multiple of 16 in [16, 128] (got %d)", n_mels);
+  WFL_CHECK_ARG(hop >= 8 && hop % 8 == 0 && hop <= kNfft, "wfl_mel_power: hop %d must be a multiple of 8 in [8, %d]", hop,
+                kNfft);
+  WFL_CHECK_ARG(out_stride >= n_mels, "wfl_mel_power: out_stride %d invalid", out_stride);
+  // reflect padding needs n_fft/2 < n_samples (torch.stft raises otherwise)
+  WFL_CHECK_ARG(n_samples > kNfft / 2 && wave_stride >= n_samples, "wfl_mel_power: n_samples %d must exceed %d",
+                n_samples, kNfft / 2);
+  if (B <= 0) return WFL_OK;
+  static bool configured = false;
+  if (!configured) {
+    WFL_CUDA(cudaFuncSetAttribute(logmel_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
+    configured = true;
+  }
+  const int frames = 1 + n_samples / hop;
+  const int64_t plane_rows = frames - 1 + (kNfft + hop - 1) / hop;  // rows of the strided view covering n + n_fft samples
+  const int64_t plane_len = plane_rows * hop;
+  {
+    dim3 grid(static_cast<unsigned>(std::min<int64_t>((plane_len + 255) / 256, 128)), B);
+    mel_prep_kernel<<<grid, 256, 0, stream>>>(wave, wave_stride, n_samples, plane_len,
+                                              static_cast<__half*>(scratch_planes));
+    WFL_CUDA(cudaGetLastError());
+  }
+  {
+    wfl_gemm_desc d = {};
+    d.a = scratch_planes;
+    d.a_rows = 2 * plane_rows;
+    d.a_cols = kNfft;
+    d.a_row_stride = hop;
+    d.a_batch_stride = 2 * plane_len;
+    d.batches = B;
+    d.w = basis_split_f16;
+    d.n = kDftCols;
+    d.slab_k = kDftCols;
+    d.num_slabs = 3;
+    d.slab_row_shift[0] = 0;
+    d.slab_row_shift[1] = 0;
+    d.slab_row_shift[2] = static_cast<int32_t>(plane_rows);
+    d.bias = nullptr;
+    d.act = WFL_ACT_NONE;
+    d.out_mode = WFL_OUT_STORE_F32;
+    d.alpha = 1.0f;
+    d.out = scratch_dft;
+    d.m_rows = frames;
+    d.out_row_stride = kDftCols;
+    d.out_batch_stride = static_cast<int64_t>(frames) * kDftCols;
+    d.tile_n = 256;
+    const int rc = wfl_gemm(&d, stream_);
+    if (rc != WFL_OK) return rc;
+  }
+  int2* span = reinterpret_cast<int2*>(scratch_span);
+  mel_span_kernel<<<1, 128, 0, stream>>>(mel_filters, n_mels, span);
+  WFL_CUDA(cudaGetLastError());
+  dim3 grid((frames + kFrameTile - 1) / kFrameTile, B);
+  logmel_post_kernel<true><<<grid, 256, kPostSmem, stream>>>(scratch_dft, frames, mel_filters, n_mels, span, out,
+                                                             out_stride, nullptr);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }

@@ -157,6 +157,21 @@ __global__ void __launch_bounds__(256) broadcast_rows_kernel(const float4* __res
   }
 }
 
+// out[r][g*w_out + j] = in[r][g*w_in + j], j < w_out: drops the zero-padded units of each direction when the BiLSTM ran
+// at a padded hidden size (hidden sizes the recurrence kernel is not built for, e.g. 40 for encoder_type "none").
+__global__ void __launch_bounds__(256) gather_cols_kernel(const float4* __restrict__ in, int64_t rows, int groups,
+                                                          int w_in4, int w_out4, float4* __restrict__ out) {
+  const int row4 = groups * w_out4;
+  const int64_t total = rows * row4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / row4;
+    const int c = static_cast<int>(i - r * row4);
+    const int g = c / w_out4, j = c - g * w_out4;
+    out[i] = in[r * (static_cast<int64_t>(groups) * w_in4) + g * w_in4 + j];
+  }
+}
+
 // Offset head tail (REF/model.py:140-141): out[r][j] = sigmoid(x[r] . w[j] + b[j]); one warp per row.
 __global__ void __launch_bounds__(256) rowdot_sigmoid_kernel(const __half* __restrict__ x, int64_t rows, int d,
                                                              const float* __restrict__ w,
@@ -275,6 +290,20 @@ extern "C" int wfl_split_f16(const float* x, int64_t rows, int32_t d, void* out_
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16));
   split_f16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(x), rows, d / 4,
                                                                         static_cast<__half*>(out_hi_lo));
+  WFL_CUDA(cudaGetLastError());
+  return WFL_OK;
+}
+
+extern "C" int wfl_gather_cols(const float* in, int64_t rows, int32_t groups, int32_t w_in, int32_t w_out, float* out,
+                               void* stream) {
+  WFL_CHECK_ARG(in && out, "wfl_gather_cols: null pointer");
+  WFL_CHECK_ARG(groups >= 1 && w_out > 0 && w_out <= w_in && w_in % 4 == 0 && w_out % 4 == 0,
+                "wfl_gather_cols: widths must be multiples of 4 with w_out <= w_in");
+  const int64_t total = rows * groups * (w_out / 4);
+  if (total <= 0) return WFL_OK;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16));
+  gather_cols_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(in), rows, groups, w_in / 4, w_out / 4, reinterpret_cast<float4*>(out));
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
 }

@@ -16,9 +16,20 @@ import torch
 
 from . import arch as _arch
 from . import ops, packing
-from .frontend import whisper_frontend_constants
+from .frontend import dft_basis_split, whisper_frontend_constants
 
 MEL_PAD = 128  # conv1 K-slab width: 80 or 128 mel channels, zero padded to two 64-element K blocks
+ATTN_HEAD_DIMS = (64, 256, 384, 512, 640)  # built instantiations of the attention kernels (csrc/attention*.cu)
+LSTM_HIDDEN = (192, 256, 384, 512, 640)  # built instantiations of the recurrence (csrc/lstm.cu)
+
+
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+def _v(t, rows, cols):
+    """[rows, cols] view over the front of a scratch buffer."""
+    return t if tuple(t.shape) == (rows, cols) else t.view(-1)[:rows * cols].view(rows, cols)
 
 
 class Engine:
@@ -28,6 +39,11 @@ class Engine:
         self.m = config["model"]
         self.arch = _arch.encoder_arch(config)
         self.d = self.arch["d"]
+        # Hidden sizes that are not multiples of 64 (encoder_type "none": d = n_mels = 80) keep their true width in
+        # every activation buffer; only the WEIGHTS are zero-padded along K to whole 64-element blocks (the A tensor
+        # maps are declared d wide, so TMA zero-fills the K-block columns past d), and per-head / per-unit blocks are
+        # padded to the built attention head dims / LSTM hidden sizes.  All of it is a no-op for Whisper and WavLM.
+        self.dk = _pad64(self.d)
         self.L = n_labels
         self.Lp = (n_labels + 7) // 8 * 8
         self.W = {}
@@ -40,7 +56,7 @@ class Engine:
         self.W[name] = packing.f16(t) if dtype == "f16" else t.detach().float().contiguous()
 
     def _pack_linear(self, name, w, b):
-        self._put(name + ".w", w, "f16")
+        self._put(name + ".w", packing.pad_k(w.float(), _pad64(w.shape[1])), "f16")
         if b is not None:
             self._put(name + ".b", b)
 
@@ -49,14 +65,22 @@ class Engine:
         self._put(name + ".b", sd[key + ".bias"])
 
     def _pack(self, sd):
-        d, m = self.d, self.m
+        d, dk, m = self.d, self.dk, self.m
         if self.arch["type"] == "whisper":
             self._pack_whisper(sd)
-        else:
+        elif self.arch["type"] == "wavlm":
             self._pack_wavlm(sd)
+        else:  # encoder_type "none": the MelSpectrogram module's own buffers (REF/model.py:85-90)
+            self.W["mel.basis"] = dft_basis_split(sd["mel_extractor.spectrogram.window"].double().cpu().numpy()).to(self.dev)
+            self._put("mel.fb", sd["mel_extractor.mel_scale.fb"])
         # lang conditioning (REF/model.py:176-180): W [d, d+E] -> W_h and a per-language bias
         w = sd["lang_proj.weight"].float()
-        self._put("lang.w", w[:, :d], "f16")
+        self._pack_linear("lang", w[:, :d], None)
+        # encoder_type "none": the hidden states are raw mel POWERS (1e-2 .. 1e4 and beyond), so their first projection
+        # (lang_proj, or the BiLSTM input GEMM when no language is given) runs in split precision like the classifier
+        self.raw_hidden = self.arch["type"] == "none"
+        if self.raw_hidden:
+            self.W["lang.w3"] = packing.split_hi_lo(w[:, :d].to(self.dev), dk)
         self._put("lang.bias", sd["lang_emb.weight"].float() @ w[:, d:].T + sd["lang_proj.bias"].float())
         if m.get("enable_bilstm", True):
             self._pack_bilstm(sd)
@@ -64,35 +88,45 @@ class Engine:
         self.ffx = m.get("conformer_ff_expansion", 4)
         self.conf_heads = m.get("conformer_heads", 4)
         self.conf_k = m.get("conformer_kernel_size", 31)
+        H = self.conf_heads
+        hd = d // H
+        hdp = self.conf_hdp = packing.fit_size(hd, ATTN_HEAD_DIMS, "Conformer head dim")
+        self.conf_aw = H * hdp  # width of the (head-padded) q / k / v / context rows
+        self.glu_tile = 256 if dk % 128 == 0 else 128
         for i in range(self.n_conf):
             p, q = f"conformer_layers.{i}.", f"conf{i}."
             for ff in ("ff1", "ff2"):
                 self._pack_ln(q + ff + ".ln", sd, p + ff + ".net.0")
                 self._pack_linear(q + ff + ".l1", sd[p + ff + ".net.1.weight"], sd[p + ff + ".net.1.bias"])
                 self._pack_linear(q + ff + ".l2", sd[p + ff + ".net.4.weight"], sd[p + ff + ".net.4.bias"])
-            self._pack_linear(q + "attn.in", sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"])
-            self._pack_linear(q + "attn.out", sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+            # q/k/v rows and out_proj columns: 3H (resp. H) head blocks, each padded to the built head dim
+            self._pack_linear(q + "attn.in", packing.pad_blocks(sd[p + "self_attn.in_proj_weight"].float(), 3 * H, hd, hdp, 0),
+                              packing.pad_blocks(sd[p + "self_attn.in_proj_bias"].float(), 3 * H, hd, hdp, 0))
+            self._pack_linear(q + "attn.out", packing.pad_blocks(sd[p + "self_attn.out_proj.weight"].float(), H, hd, hdp, 1),
+                              sd[p + "self_attn.out_proj.bias"])
             self._pack_ln(q + "ln1", sd, p + "ln1")
             self._pack_ln(q + "ln2", sd, p + "ln2")
-            wg, bg = packing.interleave_glu(sd[p + "conv.0.weight"].float()[:, :, 0], sd[p + "conv.0.bias"].float(), 256)
+            # GLU: value rows and gate rows each padded to dk (padded outputs are 0 * sigmoid(0) = 0)
+            wg, bg = packing.interleave_glu(packing.pad_blocks(sd[p + "conv.0.weight"].float()[:, :, 0], 2, d, dk, 0),
+                                            packing.pad_blocks(sd[p + "conv.0.bias"].float(), 2, d, dk, 0), self.glu_tile)
             self._pack_linear(q + "pw1", wg, bg)
             wc, bc = packing.fold_batchnorm(sd[p + "conv.2.weight"].float(), sd[p + "conv.2.bias"].float(),
                                             sd[p + "conv.3.weight"].float(), sd[p + "conv.3.bias"].float(),
                                             sd[p + "conv.3.running_mean"].float(), sd[p + "conv.3.running_var"].float())
-            self._pack_linear(q + "conv", packing.conv_taps(wc), bc)
+            self._pack_linear(q + "conv", packing.conv_taps(wc, dk), bc)
             self._pack_linear(q + "pw2", sd[p + "conv.5.weight"].float()[:, :, 0], sd[p + "conv.5.bias"])
         self.dil_depth = m.get("dilated_conv_depth", 2) if m.get("enable_dilated_conv", True) else 0
         self.dil_k = m.get("dilated_conv_kernel", 3)
         for i in range(self.dil_depth):
-            self._pack_linear(f"dil{i}", packing.conv_taps(sd[f"dilated_conv_stack.{2 * i}.weight"].float()),
+            self._pack_linear(f"dil{i}", packing.conv_taps(sd[f"dilated_conv_stack.{2 * i}.weight"].float(), dk),
                               sd[f"dilated_conv_stack.{2 * i}.bias"])
         # classifier in split precision: A = [hi | lo], W = [hi | hi | lo]  (x_hi w_hi + x_lo w_hi + x_hi w_lo)
         wc = packing.pad_rows(sd["classifier.weight"].float(), self.Lp)
-        self.W["cls.w"] = packing.split_hi_lo(wc.to(self.dev))  # f16 [Lp, 3d]
+        self.W["cls.w"] = packing.split_hi_lo(wc.to(self.dev), dk)  # f16 [Lp, 3 dk]
         bc = torch.zeros(self.Lp, device=self.dev)
         bc[:self.L] = sd["classifier.bias"].float().to(self.dev)
         self.W["cls.b"] = bc
-        self._pack_linear("off.conv", packing.conv_taps(sd["boundary_offset_head.0.weight"].float()),
+        self._pack_linear("off.conv", packing.conv_taps(sd["boundary_offset_head.0.weight"].float(), dk),
                           sd["boundary_offset_head.0.bias"])
         self._put("off.w", sd["boundary_offset_head.2.weight"].float()[:, :, 0])
         self._put("off.b", sd["boundary_offset_head.2.bias"])
@@ -186,17 +220,26 @@ class Engine:
         """nn.LSTM weights (REF/model.py:105-111): W_ih rows re-ordered [unit][gate] per direction so the recurrence
         reads its four gate pre-activations as one float4; b_ih + b_hh folded into the input GEMM's bias."""
         d = self.d
-        Hs = d // 2
+        Hs = self.lstm_h = d // 2
+        # hidden sizes the recurrence is not built for run zero-padded: a padded unit has zero weights and bias, so
+        # its cell state and output stay exactly 0 (c = 0.5 c + 0.5 tanh(0), h = 0.5 tanh(c))
+        Hp = self.lstm_hp = packing.fit_size(Hs, LSTM_HIDDEN, "BiLSTM hidden size")
         self.lstm_layers = self.m.get("bilstm_num_layer", 1)
         for layer in range(self.lstm_layers):
             w_in, b_in, w_hh = [], [], []
             for suffix in ("", "_reverse"):
                 w_ih = sd[f"bilstm.weight_ih_l{layer}{suffix}"].float()
-                w_in.append(w_ih.view(4, Hs, -1).permute(1, 0, 2).reshape(4 * Hs, -1))
+                if layer > 0:  # input = [fwd | bwd] of the layer below, each Hp wide here
+                    w_ih = packing.pad_blocks(w_ih, 2, Hs, Hp, 1)
+                w_ih = w_ih.view(4, Hs, -1).permute(1, 0, 2).reshape(4 * Hs, -1)  # rows [unit][gate]
+                w_in.append(packing.pad_rows(w_ih, 4 * Hp))
                 b = sd[f"bilstm.bias_ih_l{layer}{suffix}"].float() + sd[f"bilstm.bias_hh_l{layer}{suffix}"].float()
-                b_in.append(b.view(4, Hs).t().reshape(-1))
-                w_hh.append(sd[f"bilstm.weight_hh_l{layer}{suffix}"].float())
+                b_in.append(packing.pad_rows(b.view(4, Hs).t().reshape(-1, 1), 4 * Hp).reshape(-1))
+                w = packing.pad_blocks(sd[f"bilstm.weight_hh_l{layer}{suffix}"].float(), 4, Hs, Hp, 0)
+                w_hh.append(packing.pad_k(w, Hp))
             self._pack_linear(f"lstm{layer}.in", torch.cat(w_in, 0), torch.cat(b_in, 0))
+            if layer == 0 and self.raw_hidden:
+                self.W["lstm0.in.w3"] = packing.split_hi_lo(torch.cat(w_in, 0).to(self.dev), self.dk)
             self._put(f"lstm{layer}.whh", torch.stack(w_hh, 0), "f16")
 
     # ------------------------------------------------------------------------------------ workspaces
@@ -206,24 +249,30 @@ class Engine:
         if ws is not None:
             return ws
         d, dev, M = self.d, self.dev, B * T
-        F = max(self.arch["ffn"], self.ffx * d, 2 * d)
+        F = max(self.arch.get("ffn", 0), self.ffx * d, 2 * d)
+        bilstm = self.m.get("enable_bilstm", True)
         bf = dict(device=dev, dtype=torch.float16)
         ws = {
             "x": torch.empty(B, T, d, device=dev),
             "h": torch.empty(M, d, **bf),
-            "qkv": torch.empty(M, 3 * d, **bf),
-            "ctx": torch.empty(M, d, **bf),
+            "qkv": torch.empty(M, 3 * max(d, self.conf_aw), **bf),
+            "ctx": torch.empty(M, max(d, self.conf_aw, 2 * self.lstm_hp if bilstm else 0), **bf),
             "u": torch.empty(M, F, **bf),
-            "g": torch.empty(M, d, **bf),
+            "g": torch.empty(M, self.dk, **bf),
             "c": torch.empty(M, d, **bf),
             "hl": torch.empty(M, 2 * d, **bf),
             "y": torch.empty(B, T, d, device=dev),
             "logits": torch.empty(B, T, self.Lp, device=dev),
             "offsets": torch.empty(B, T, 2, device=dev),
         }
-        if self.m.get("enable_bilstm", True):
-            ws["gx"] = torch.empty(M, 4 * d, device=dev)
-        if self.arch["type"] == "whisper":
+        if bilstm:
+            ws["gx"] = torch.empty(M, 8 * self.lstm_hp, device=dev)
+            if self.lstm_hp != self.lstm_h:
+                ws["ylstm"] = torch.empty(M, 2 * self.lstm_hp, device=dev)
+        if self.arch["type"] == "none":
+            if n_samples is not None:
+                ws["mel_scratch"] = ops.mel_power_scratch(B, n_samples, self.arch["hop"], dev)
+        elif self.arch["type"] == "whisper":
             ws["wave"] = torch.zeros(B, 480000, device=dev)
             ws["feats"] = torch.empty(B, 3000, MEL_PAD, **bf)
             ws["h1"] = torch.empty(B, 3000, d, **bf)
@@ -252,7 +301,7 @@ class Engine:
     def _linear(self, a, name, out, M, K, **kw):
         """Flat [M, K] @ W^T over all B*T rows."""
         w = self.W[name + ".w"]
-        ops.gemm(a, w, out, n=w.shape[0], slab_k=K, a_rows=M, a_cols=K, a_row_stride=a.stride(-2), m_rows=M,
+        ops.gemm(a, w, out, n=w.shape[0], slab_k=w.shape[1], a_rows=M, a_cols=K, a_row_stride=a.stride(-2), m_rows=M,
                  out_row_stride=out.stride(-2), bias=self.W.get(name + ".b"), **kw)
 
     def _conv(self, a, name, out, B, T, C, taps, dil, *, a_row_stride=None, out_row_stride=None, **kw):
@@ -261,7 +310,7 @@ class Engine:
         pad = dil * (taps - 1) // 2
         ars = C if a_row_stride is None else a_row_stride
         ors = w.shape[0] if out_row_stride is None else out_row_stride
-        ops.gemm(a, w, out, n=w.shape[0], slab_k=C, shifts=[j * dil - pad for j in range(taps)], cols=[0] * taps,
+        ops.gemm(a, w, out, n=w.shape[0], slab_k=_pad64(C), shifts=[j * dil - pad for j in range(taps)], cols=[0] * taps,
                  a_rows=T, a_cols=C, a_row_stride=ars, a_batch_stride=T * ars, batches=B, m_rows=T,
                  out_row_stride=ors, out_batch_stride=T * ors, bias=self.W.get(name + ".b"), **kw)
 
@@ -291,13 +340,14 @@ class Engine:
                  out_batch_stride=T * d, bias=self.W["enc.conv2.b"], act=ops.ACT_GELU, out_mode=ops.OUT_ADD_F32)
         H = a["heads"]
         hd = d // H
+        qkv, ctx = _v(ws["qkv"], M, 3 * d), _v(ws["ctx"], M, d)
         for i in range(a["layers"]):
             q = f"enc{i}."
             self._ln(x, q + "ln1", out_f16=ws["h"])
-            self._linear(ws["h"], q + "qkv", ws["qkv"], M, d)
-            ops.attention(ws["qkv"].view(B, T, 3 * d), ws["ctx"].view(B, T, d), B=B, T=T, H=H, hd=hd,
+            self._linear(ws["h"], q + "qkv", qkv, M, d)
+            ops.attention(qkv.view(B, T, 3 * d), ctx.view(B, T, d), B=B, T=T, H=H, hd=hd,
                           scale=hd ** -0.5, q_col=0, k_col=d, v_col=2 * d)
-            self._linear(ws["ctx"], q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
+            self._linear(ctx, q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
             self._ln(x, q + "ln2", out_f16=ws["h"])
             self._linear(ws["h"], q + "fc1", ws["u"], M, d, act=ops.ACT_GELU)
             self._linear(ws["u"], q + "fc2", x, M, a["ffn"], out_mode=ops.OUT_ADD_F32)
@@ -358,18 +408,19 @@ class Engine:
         H = a["heads"]
         hd = d // H
         tab = self._rel_bias_table(T)
+        qkv, ctx = _v(ws["qkv"], M, 3 * d), _v(ws["ctx"], M, d)
         if not large:
             self._ln(x, "wl.enc.ln", out_f32=x, out_f16=ws["h"])
         for i in range(a["layers"]):
             q = f"wl{i}."
             if large:
                 self._ln(x, q + "ln1", out_f16=ws["h"])
-            self._linear(ws["h"], q + "qkv", ws["qkv"], M, d)
+            self._linear(ws["h"], q + "qkv", qkv, M, d)
             ops.wavlm_gate(ws["h"], d, B, T, H, hd, self.W[q + "gate.w"], self.W[q + "gate.b"], self.W[q + "gate.c"],
                            ws["gate"])
-            ops.attention(ws["qkv"].view(B, T, 3 * d), ws["ctx"].view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5,
+            ops.attention(qkv.view(B, T, 3 * d), ctx.view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5,
                           q_col=0, k_col=d, v_col=2 * d, rel_bias=tab, gate=ws["gate"])
-            self._linear(ws["ctx"], q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
+            self._linear(ctx, q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
             if large:
                 self._ln(x, q + "ln2", out_f16=ws["h"])
             else:
@@ -378,6 +429,21 @@ class Engine:
             self._linear(ws["u"], q + "fc2", x, M, a["ffn"], out_mode=ops.OUT_ADD_F32)
             if not large:
                 self._ln(x, q + "ln2", out_f32=x, out_f16=ws["h"])
+        return ws, T
+
+    def _mel_features(self, wave, B):
+        """REF/model.py:149-150: hidden_states = MelSpectrogram(wave).transpose(1, 2), i.e. x [B, 1 + N // hop, n_mels]
+        fp32 is the residual stream itself; ws["hl"] receives its f16 split (lang_proj / BiLSTM operand)."""
+        a = self.arch
+        n = wave.shape[1]
+        if n <= 200:  # torch.stft's reflect padding (n_fft / 2 per side) needs a longer clip; the reference raises too
+            raise ValueError(f"clip of {n} samples is shorter than the STFT's reflect padding (200 samples)")
+        T = ops.mel_power_frames(n, a["hop"])
+        ws = self._buffers(B, T, n)
+        if wave.dtype != torch.float32 or not wave.is_contiguous():
+            wave = wave.float().contiguous()
+        ops.mel_power(wave, n, a["hop"], self.W["mel.basis"], self.W["mel.fb"], a["mels"], ws["x"], ws["mel_scratch"])
+        ops.split_f16(ws["x"], ws["hl"])
         return ws, T
 
     # ------------------------------------------------------------------------------------ conformer
@@ -394,18 +460,19 @@ class Engine:
         ops.split_f16(x, ws["hl"])
         hi = ws["hl"]
         w = self.W[q + "attn.in.w"]
-        ops.gemm(hi, w, ws["qkv"], n=3 * d, slab_k=d, a_rows=M, a_cols=d, a_row_stride=2 * d, m_rows=M,
-                 out_row_stride=3 * d, bias=self.W[q + "attn.in.b"])
+        aw = self.conf_aw
+        qkv, ctx = _v(ws["qkv"], M, 3 * aw), _v(ws["ctx"], M, aw)
+        ops.gemm(hi, w, qkv, n=3 * aw, slab_k=self.dk, a_rows=M, a_cols=d, a_row_stride=2 * d, m_rows=M,
+                 out_row_stride=3 * aw, bias=self.W[q + "attn.in.b"])
         H = self.conf_heads
-        hd = d // H
-        ops.attention(ws["qkv"].view(B, T, 3 * d), ws["ctx"].view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5,
-                      q_col=0, k_col=d, v_col=2 * d)
-        self._linear(ws["ctx"], q + "attn.out", x, M, d, out_mode=ops.OUT_ADD_F32)
+        ops.attention(qkv.view(B, T, 3 * aw), ctx.view(B, T, aw), B=B, T=T, H=H, hd=self.conf_hdp, scale=(d // H) ** -0.5,
+                      q_col=0, k_col=aw, v_col=2 * aw)
+        self._linear(ctx, q + "attn.out", x, M, aw, out_mode=ops.OUT_ADD_F32)
         ops.layernorm(x, self.W[q + "ln1.g"], self.W[q + "ln1.b"], out_f32=x, out_f16=ws["h"],
                       gamma2=self.W[q + "ln2.g"], beta2=self.W[q + "ln2.b"])
         # conv module: pw1 -> GLU -> conv-k (BatchNorm folded) -> GELU -> pw2;  x += conv
-        self._linear(ws["h"], q + "pw1", ws["g"], M, d, out_mode=ops.OUT_GLU_F16, tile_n=256)
-        self._conv(ws["g"], q + "conv", ws["c"], B, T, d, self.conf_k, 1, act=ops.ACT_GELU)
+        self._linear(ws["h"], q + "pw1", ws["g"], M, d, out_mode=ops.OUT_GLU_F16, tile_n=self.glu_tile)
+        self._conv(ws["g"], q + "conv", ws["c"], B, T, d, self.conf_k, 1, a_row_stride=self.dk, act=ops.ACT_GELU)
         self._linear(ws["c"], q + "pw2", x, M, d, out_mode=ops.OUT_ADD_F32)
         # x += 0.5 * FF2(x)
         self._ln(x, q + "ff2.ln", out_f16=ws["h"])
@@ -427,9 +494,11 @@ class Engine:
         d = self.d
         enc = ws.get("enc")
         if enc is None:
-            enc = ws["enc"] = torch.empty(B * T, d, device=self.dev, dtype=torch.float16)
+            enc = ws["enc"] = torch.empty(B * T, 2 * d if self.raw_hidden else d, device=self.dev, dtype=torch.float16)
         if final_ln is not None:
             self._ln(ws["x"], final_ln, out_f16=enc)
+        elif self.raw_hidden:
+            enc.copy_(ws["hl"])  # the [hi | lo] split of x that _encode left
         else:
             enc.copy_(ws["h"])  # wavlm-base(-plus): the last post-LN already left f16(x) in ws["h"]
         outs = []
@@ -439,9 +508,12 @@ class Engine:
             outs.append((logits.clone(), offsets.clone()))
         return outs
 
-    def _encode(self, wave):
+    def _require_device(self, wave):
         if not wave.is_cuda:
             raise RuntimeError("wfl_asr_b200 has no CPU path: input_values must be a CUDA tensor")
+
+    def _encode(self, wave):
+        self._require_device(wave)
         if wave.dim() != 2:
             raise ValueError("input_values must be [batch, samples]")
         B = wave.shape[0]
@@ -449,6 +521,9 @@ class Engine:
             ws = self._buffers(B, 1500)
             T = self._whisper_encoder(wave, ws, B)
             final_ln = "enc.ln"
+        elif self.arch["type"] == "none":
+            ws, T = self._mel_features(wave, B)
+            final_ln = None
         else:
             ws, T = self._wavlm_encoder(wave, B)
             # wavlm-large ends with encoder.layer_norm; wavlm-base(-plus) is post-LN: x is final and ws["h"] = f16(x)
@@ -462,14 +537,16 @@ class Engine:
         x = ws["x"]
         M = B * T
         bilstm = self.m.get("enable_bilstm", True)
-        lstm_in = ws["h"]
+        # f16 copy of a final_ln-free encoder output: ws["h"] (wavlm-base post-LN) or the hi half of ws["hl"] ("none")
+        raw = self.raw_hidden
+        f16_x, f16_stride = (ws["hl"], 2 * d) if raw else (ws["h"], d)
+        lstm_in = f16_x if final_ln is None else ws["h"]
+        lstm_split = raw and lang_id is None  # the BiLSTM consumes the raw [hi | lo] hidden states directly
         if enc is not None:
-            self._lang_proj(enc, d, lang_id, ws, B, T, bilstm)
-            lstm_in = ws["g"]
+            lstm_in = self._lang_proj(enc, enc.shape[1], lang_id, ws, B, T, bilstm)
         elif final_ln is None and max_label_len is None:
             if lang_id is not None:
-                self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
-                lstm_in = ws["g"]
+                lstm_in = self._lang_proj(f16_x, f16_stride, lang_id, ws, B, T, bilstm)
         elif max_label_len is not None:
             # REF/model.py:166-174 (training/eval only): fix T to the label length; rare path, torch glue
             if final_ln is not None:
@@ -484,15 +561,15 @@ class Engine:
             x, T, M = ws["x"], mll, B * mll
             ops.split_f16(x, ws["hl"])
             if lang_id is not None:
-                self._lang_proj(ws["hl"], 2 * d, lang_id, ws, B, T, bilstm)
-                lstm_in = ws["g"]
+                lstm_in = self._lang_proj(ws["hl"], 2 * d, lang_id, ws, B, T, bilstm)
+            elif bilstm and raw:
+                lstm_in = ws["hl"]
             elif bilstm:
                 ws["h"].view(B, T, d).copy_(ws["hl"].view(B, T, 2 * d)[:, :, :d])
                 lstm_in = ws["h"]
         elif lang_id is not None:
             self._ln(x, final_ln, out_f16=ws["h"])
-            self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
-            lstm_in = ws["g"]
+            lstm_in = self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
         elif bilstm:
             self._ln(x, final_ln, out_f16=ws["h"])
         else:
@@ -500,13 +577,23 @@ class Engine:
         if bilstm:
             # REF/model.py:182-183: input projection for all steps as one GEMM, then the serial recurrence
             a_in = lstm_in
-            Hs = d // 2
+            Hs, Hp = self.lstm_h, self.lstm_hp
+            y_mid = _v(ws["ctx"], M, 2 * Hp)
+            y_last = x if Hp == Hs else ws["ylstm"]
             for layer in range(self.lstm_layers):
                 last = layer == self.lstm_layers - 1
-                self._linear(a_in, f"lstm{layer}.in", ws["gx"], M, d, out_mode=ops.OUT_STORE_F32)
-                ops.lstm_layer(ws["gx"], self.W[f"lstm{layer}.whh"], B, T, Hs,
-                               y_f16=None if last else ws["ctx"], y_f32=x if last else None)
-                a_in = ws["ctx"]
+                if layer == 0 and lstm_split:
+                    ops.gemm(a_in, self.W["lstm0.in.w3"], ws["gx"], n=8 * Hp, slab_k=self.dk, shifts=[0, 0, 0],
+                             cols=[0, d, 0], a_rows=M, a_cols=2 * d, a_row_stride=2 * d, m_rows=M, out_row_stride=8 * Hp,
+                             bias=self.W["lstm0.in.b"], out_mode=ops.OUT_STORE_F32)
+                else:
+                    self._linear(a_in, f"lstm{layer}.in", ws["gx"], M, d if layer == 0 else 2 * Hp,
+                                 out_mode=ops.OUT_STORE_F32)
+                ops.lstm_layer(ws["gx"], self.W[f"lstm{layer}.whh"], B, T, Hp,
+                               y_f16=None if last else y_mid, y_f32=y_last if last else None)
+                a_in = y_mid
+            if Hp != Hs:  # drop the padded units of each direction: [fwd Hp | bwd Hp] -> [fwd Hs | bwd Hs] = x
+                ops.gather_cols(ws["ylstm"], x, 2, Hp, Hs)
         for i in range(self.n_conf):
             self._conformer(i, ws, B, T)
         # tail: dilated stack -> classifier (split precision) + boundary-offset head
@@ -522,7 +609,7 @@ class Engine:
                 a_in, ars = out, d
             src = ws["y"]
         ops.split_f16(src, ws["hl"])
-        ops.gemm(ws["hl"], self.W["cls.w"], ws["logits"], n=self.Lp, slab_k=d, shifts=[0, 0, 0], cols=[0, d, 0],
+        ops.gemm(ws["hl"], self.W["cls.w"], ws["logits"], n=self.Lp, slab_k=self.dk, shifts=[0, 0, 0], cols=[0, d, 0],
                  a_rows=M, a_cols=2 * d, a_row_stride=2 * d, m_rows=M, out_row_stride=self.Lp, bias=self.W["cls.b"],
                  out_mode=ops.OUT_STORE_F32, tile_n=128)
         self._conv(ws["hl"], "off.conv", ws["c"], B, T, d, 3, 1, a_row_stride=2 * d, act=ops.ACT_GELU)
@@ -538,7 +625,13 @@ class Engine:
         if lang_id.numel() != B:
             raise ValueError("lang_id must have one entry per batch item")
         bias = self.W["lang.bias"].index_select(0, lang_id).contiguous()  # [B, d]
-        ops.gemm(a, self.W["lang.w"], ws["g"] if to_f16 else ws["x"], n=d, slab_k=d, a_rows=T, a_cols=d,
-                 a_row_stride=a_row_stride, a_batch_stride=T * a_row_stride, batches=B, m_rows=T, out_row_stride=d,
-                 out_batch_stride=T * d, bias=bias, bias_batch_stride=d,
-                 out_mode=ops.OUT_STORE_F16 if to_f16 else ops.OUT_STORE_F32)
+        out = _v(ws["g"], B * T, d) if to_f16 else ws["x"]
+        if self.raw_hidden:  # a = [hi | lo] of the raw hidden states: x_hi w_hi + x_lo w_hi + x_hi w_lo
+            assert a_row_stride == 2 * d
+            w, slabs = self.W["lang.w3"], dict(shifts=[0, 0, 0], cols=[0, d, 0], a_cols=2 * d)
+        else:
+            w, slabs = self.W["lang.w"], dict(a_cols=d)
+        ops.gemm(a, w, out, n=d, slab_k=self.dk, a_rows=T, a_row_stride=a_row_stride, a_batch_stride=T * a_row_stride,
+                 batches=B, m_rows=T, out_row_stride=d, out_batch_stride=T * d, bias=bias, bias_batch_stride=d,
+                 out_mode=ops.OUT_STORE_F16 if to_f16 else ops.OUT_STORE_F32, **slabs)
+        return out

@@ -141,6 +141,22 @@ def _wavlm_holder(a):
     return root
 
 
+def _mel_holder(a):
+    """Buffer names of torchaudio.transforms.MelSpectrogram (REF/model.py:85-90): spectrogram.window, mel_scale.fb."""
+    from .frontend import N_FFT, htk_mel_filters
+    if a["hop"] % 8 != 0 or not 8 <= a["hop"] <= N_FFT:
+        raise ValueError(f"encoder_type 'none': hop length {a['hop']} (frame_duration * sample_rate) must be a multiple "
+                         f"of 8 in [8, {N_FFT}]")
+    if a["mels"] % 16 != 0 or not 16 <= a["mels"] <= 128:
+        raise ValueError(f"encoder_type 'none': n_mels {a['mels']} must be a multiple of 16 in [16, 128]")
+    root = nn.Module()
+    root.spectrogram = nn.Module()
+    root.spectrogram.register_buffer("window", torch.hann_window(N_FFT))
+    root.mel_scale = nn.Module()
+    root.mel_scale.register_buffer("fb", htk_mel_filters(a["mels"], N_FFT // 2 + 1, a["sample_rate"]))
+    return root
+
+
 class BIOPhonemeTagger(nn.Module):
     """Same constructor, attributes and ``forward`` contract as REF/model.py:55-201."""
 
@@ -149,9 +165,6 @@ class BIOPhonemeTagger(nn.Module):
         m = config["model"]
         self.config = config
         self.encoder_type = m["encoder_type"].lower()
-        if self.encoder_type in ("none", "null"):
-            raise ValueError("encoder_type 'none' (raw mel front-end, REF/model.py:82-91) is not on the B200 "
-                             "labeling path yet; use 'whisper' or 'wavlm'.")
         self.arch = _arch.encoder_arch(config)  # raises ValueError for unknown types like the reference
         self.freeze_encoder = m.get("freeze_encoder", False)
         self.enable_bilstm = m.get("enable_bilstm", True)
@@ -163,7 +176,12 @@ class BIOPhonemeTagger(nn.Module):
         d = self.arch["d"]
         self.hidden_size = d
 
-        self.encoder = _whisper_holder(self.arch) if self.encoder_type == "whisper" else _wavlm_holder(self.arch)
+        if self.arch["type"] == "none":
+            self.encoder = None
+            self.feature_extractor = None
+            self.mel_extractor = _mel_holder(self.arch)
+        else:
+            self.encoder = _whisper_holder(self.arch) if self.encoder_type == "whisper" else _wavlm_holder(self.arch)
         self.lang_emb_dim = m.get("lang_emb_dim", 64)
         self.lang_emb = nn.Embedding(m["num_languages"], self.lang_emb_dim)
         self.lang_proj = nn.Linear(d + self.lang_emb_dim, d)

@@ -165,6 +165,35 @@ def whisper_logmel(wave, n_samples, basis_split, filters, n_mels, out, scratch):
     _count(5)  # prep, DFT GEMM, filter spans, power + mel + log, normalise
 
 
+def mel_power_frames(n_samples, hop):
+    return 1 + n_samples // hop
+
+
+def mel_power_scratch(B, n_samples, hop, device):
+    """Scratch buffers of wfl_mel_power: (planes f16, dft fp32 [B, frames, 448], filter spans)."""
+    frames = mel_power_frames(n_samples, hop)
+    plane = (frames - 1 + (400 + hop - 1) // hop) * hop
+    return (torch.empty(2 * plane * B + 4096, dtype=torch.float16, device=device),
+            torch.empty(B, frames, 448, device=device), torch.empty(256, device=device))
+
+
+def mel_power(wave, n_samples, hop, basis_split, filters, n_mels, out, scratch):
+    """wave fp32 [B, >= n_samples] -> out fp32 [B, 1 + n_samples // hop, >= n_mels] (MelSpectrogram power, transposed)."""
+    planes, dft, span = scratch
+    rc = _lib.load().wfl_mel_power(_ptr(wave), wave.stride(0), n_samples, wave.shape[0], hop, _ptr(basis_split),
+                                   _ptr(filters), n_mels, _ptr(out), out.stride(-2), _ptr(planes), _ptr(dft), _ptr(span),
+                                   _stream())
+    _lib.check(rc, "wfl_mel_power")
+    _count(4)  # prep, DFT GEMM, filter spans, power + mel
+
+
+def gather_cols(src, dst, groups, w_in, w_out):
+    """dst[r, g*w_out + j] = src[r, g*w_in + j] (fp32)."""
+    rows = src.numel() // (groups * w_in)
+    _lib.check(_lib.load().wfl_gather_cols(_ptr(src), rows, groups, w_in, w_out, _ptr(dst), _stream()), "wfl_gather_cols")
+    _count()
+
+
 def decode_frames(logits2d, L, o_id, threshold, ids):
     rows = logits2d.shape[0]
     rc = _lib.load().wfl_decode_frames(_ptr(logits2d), rows, L, logits2d.stride(0), o_id, threshold, _ptr(ids), _stream())

@@ -19,10 +19,39 @@ def f16(t):
     return t.detach().float().clamp(-F16_MAX, F16_MAX).to(torch.float16).contiguous()
 
 
-def conv_taps(weight):
-    """[out, in, k] -> [out, k*in] with tap-major K (tap j multiplies input row t + j*dil - pad)."""
+def conv_taps(weight, in_to=None):
+    """[out, in, k] -> [out, k*in] with tap-major K (tap j multiplies input row t + j*dil - pad).  ``in_to``: zero-pad
+    every tap's input channels to this width (one tap = one K slab, whose width must be a multiple of 64)."""
     o, i, k = weight.shape
-    return weight.permute(0, 2, 1).reshape(o, k * i).contiguous()
+    w = weight.permute(0, 2, 1)
+    if in_to is not None and in_to != i:
+        wp = w.new_zeros(o, k, in_to)
+        wp[:, :, :i] = w
+        w, i = wp, in_to
+    return w.reshape(o, k * i).contiguous()
+
+
+def pad_blocks(t, blocks, width, width_to, dim):
+    """Dimension ``dim`` holds ``blocks`` consecutive blocks of ``width`` entries; zero-pad each block to ``width_to``
+    (attention heads padded to a built head size, LSTM units padded to a built hidden size)."""
+    if width == width_to:
+        return t
+    shape = list(t.shape)
+    assert shape[dim] == blocks * width
+    v = t.reshape(shape[:dim] + [blocks, width] + shape[dim + 1:])
+    out_shape = list(v.shape)
+    out_shape[dim + 1] = width_to
+    out = v.new_zeros(out_shape)
+    out.narrow(dim + 1, 0, width).copy_(v)
+    return out.reshape(shape[:dim] + [blocks * width_to] + shape[dim + 1:])
+
+
+def fit_size(n, built, what):
+    """Smallest built kernel size >= n (operands are zero-padded up to it)."""
+    for s in built:
+        if s >= n:
+            return s
+    raise ValueError(f"{what} {n} exceeds the largest built size {built[-1]}")
 
 
 def pad_k(weight2d, k_to):
@@ -54,10 +83,13 @@ def interleave_glu(weight2d, bias, tile_n):
     return weight2d[idx].contiguous(), (bias[idx].contiguous() if bias is not None else None)
 
 
-def split_hi_lo(weight2d):
-    """fp32 [n, k] -> f16 [n, 3k] = [hi | hi | lo]: pairs with A = [hi | lo] slabs (cols 0, k, 0)."""
+def split_hi_lo(weight2d, k_to=None):
+    """fp32 [n, k] -> f16 [n, 3k] = [hi | hi | lo]: pairs with A = [hi | lo] slabs (cols 0, k, 0).  ``k_to``: zero-pad
+    each of the three slabs to this width."""
     hi = f16(weight2d)
     lo = f16(weight2d.float() - hi.float())
+    if k_to is not None:
+        hi, lo = pad_k(hi, k_to), pad_k(lo, k_to)
     return torch.cat([hi, hi, lo], dim=1).contiguous()
 
 

@@ -15,9 +15,11 @@ import torch.distributed as dist
 from .pipeline import SEG_DTYPE
 
 
-def frames_for(n_samples, encoder_type):
+def frames_for(n_samples, encoder_type, hop=320):
     if encoder_type == "whisper":
         return 1500  # Whisper pads/truncates every clip to 30 s
+    if encoder_type in ("none", "null"):
+        return 1 + n_samples // hop  # MelSpectrogram with center=True (REF/model.py:85-90)
     n = n_samples
     for k, s in zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2)):
         n = (n - k) // s + 1
