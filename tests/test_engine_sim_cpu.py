@@ -86,3 +86,18 @@ def test_whisper_engine_through_the_simulator(monkeypatch):
     eng, logits, offsets = _run(monkeypatch, cfg, sd, labels, wave, lang)
     ref_l, ref_o = to.forward(wave, sd, cfg, lang)
     _check(logits, offsets, ref_l, ref_o)
+
+
+def test_sub_batched_forward_layout(monkeypatch):
+    """WFL_SUB_BATCH: the batch in equal parts writing straight into the full-size outputs (bitwise equality with the
+    single pass is a property of the real kernels and is asserted on the GPU; here: same values, right slices)."""
+    cfg, labels, sd, wave, lang = mfg.case_inputs("mel_none_full")
+    ops_sim.install(monkeypatch)
+    eng = Engine(sd, cfg, len(labels), CPU)
+    monkeypatch.setenv("WFL_SUB_BATCH", "0")
+    one_l, one_o = (t.clone() for t in eng.forward(wave, lang))
+    monkeypatch.setenv("WFL_SUB_BATCH", "1")
+    l, o = eng.forward(wave, lang)
+    # torch's CPU matmul is not batch-invariant and an fp16 rounding flip propagates: layout-level tolerance
+    assert l.shape == one_l.shape and (l - one_l).abs().max().item() <= 1e-3 * one_l.abs().max().item()
+    assert (o - one_o).abs().max().item() <= 1e-4

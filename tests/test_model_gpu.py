@@ -100,6 +100,25 @@ def test_language_mean_fast_path(name):
     assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
 
 
+def test_sub_batched_forward_is_bitwise_identical(monkeypatch):
+    """engine.forward may push a large batch through in equal sub-batches (L2-resident working set, DESIGN.md section 3);
+    clips are independent and the kernels batch-invariant, so the result must equal the single pass bit for bit."""
+    cfg, labels, sd, wave, lang, model = _build("whisper_base_cfg2")
+    wave4 = torch.cat([wave, wave.flip(0) * 0.5, wave * 0.25, wave.flip(0)], dim=0)[:4].contiguous().to(DEV)
+    lang4 = torch.tensor([0, 1, 1, 0], device=DEV)
+    monkeypatch.setenv("WFL_SUB_BATCH", "0")
+    one_l, one_o = (t.clone() for t in model(wave4, lang4))
+    for step in ("2", "1"):
+        monkeypatch.setenv("WFL_SUB_BATCH", step)
+        l, o = model(wave4, lang4)
+        assert torch.equal(l, one_l) and torch.equal(o, one_o), f"sub-batches of {step} differ from the single pass"
+    monkeypatch.setenv("WFL_SUB_BATCH", "2")
+    l, o = model(wave4, None)
+    monkeypatch.setenv("WFL_SUB_BATCH", "0")
+    l1, o1 = model(wave4, None)
+    assert torch.equal(l, l1) and torch.equal(o, o1)
+
+
 def test_cpu_input_fails_loudly():
     cfg, labels, sd, wave, lang, model = _build("whisper_base_cfg2")
     with pytest.raises(RuntimeError):

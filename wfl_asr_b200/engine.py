@@ -11,6 +11,7 @@ Reference call order followed: REF/model.py:148-194 (forward), :40-52 (Conformer
 TF/models/whisper/modeling_whisper.py:593-647, TF/models/wavlm/modeling_wavlm.py:1039-1095.
 """
 import math
+import os
 
 import torch
 
@@ -48,6 +49,7 @@ class Engine:
         self.Lp = (n_labels + 7) // 8 * 8
         self.W = {}
         self._ws = {}
+        self._full_out = {}
         self._pack(sd)
 
     # ------------------------------------------------------------------------------------ packing
@@ -482,8 +484,36 @@ class Engine:
     # ------------------------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, wave, lang_id=None, max_label_len=None):
-        ws, B, T, final_ln = self._encode(wave)
-        return self._head(ws, B, T, final_ln, lang_id, max_label_len)
+        step = self._sub_batch(wave.shape[0]) if max_label_len is None and wave.dim() == 2 else 0
+        if not step:
+            ws, B, T, final_ln = self._encode(wave)
+            return self._head(ws, B, T, final_ln, lang_id, max_label_len)
+        # The batch goes through in equal sub-batches whose per-layer working set stays in L2: clips are independent
+        # and every kernel is batch-invariant (section 5 of DESIGN.md), so the result is bit-identical to one pass.
+        B = wave.shape[0]
+        if lang_id is not None:
+            lang_id = lang_id.to(self.dev).long().view(-1)
+            if lang_id.numel() != B:
+                raise ValueError("lang_id must have one entry per batch item")
+        full = None
+        for b0 in range(0, B, step):
+            ws, Bc, T, final_ln = self._encode(wave[b0:b0 + step])
+            if full is None:
+                full = self._full_out.get((B, T))
+                if full is None:
+                    full = (torch.empty(B, T, self.Lp, device=self.dev), torch.empty(B, T, 2, device=self.dev))
+                    self._full_out = {(B, T): full}
+            self._head(ws, Bc, T, final_ln, None if lang_id is None else lang_id[b0:b0 + step], None,
+                       dest=(full[0][b0:b0 + step], full[1][b0:b0 + step]))
+        return full[0][:, :, :self.L], full[1]
+
+    def _sub_batch(self, B):
+        """Clips per sub-batch (0 = the whole batch in one pass, the default).  WFL_SUB_BATCH=n splits into parts of n.
+        Measured on the bench workload (32 x 30 s, profiles/README.md): parts of 16 keep a layer's working set inside
+        L2 but run the same number of GEMM tile rounds and twice the launches -- 10.44 ms against 10.15 ms in one pass,
+        so no automatic rule turns it on; the switch stays for memory-bound deployments and as a batch-invariance probe."""
+        step = int(os.environ.get("WFL_SUB_BATCH", "0") or 0)
+        return step if 0 < step < B and B % step == 0 else 0
 
     @torch.no_grad()
     def forward_languages(self, wave, lang_ids):
@@ -530,7 +560,7 @@ class Engine:
             final_ln = "wl.enc.ln" if self.arch["stable_ln"] else None
         return ws, B, T, final_ln
 
-    def _head(self, ws, B, T, final_ln, lang_id, max_label_len, enc=None):
+    def _head(self, ws, B, T, final_ln, lang_id, max_label_len, enc=None, dest=None):
         """Everything after the encoder (REF/model.py:166-194).  ``enc``: f16 encoder output kept by
         forward_languages (final LayerNorm already applied); otherwise it is produced here from ws["x"] / ws["h"]."""
         d = self.d
@@ -608,13 +638,14 @@ class Engine:
                            out_mode=ops.OUT_STORE_F32 if last else ops.OUT_STORE_F16)
                 a_in, ars = out, d
             src = ws["y"]
+        logits, offsets = (ws["logits"], ws["offsets"]) if dest is None else dest
         ops.split_f16(src, ws["hl"])
-        ops.gemm(ws["hl"], self.W["cls.w"], ws["logits"], n=self.Lp, slab_k=self.dk, shifts=[0, 0, 0], cols=[0, d, 0],
+        ops.gemm(ws["hl"], self.W["cls.w"], logits, n=self.Lp, slab_k=self.dk, shifts=[0, 0, 0], cols=[0, d, 0],
                  a_rows=M, a_cols=2 * d, a_row_stride=2 * d, m_rows=M, out_row_stride=self.Lp, bias=self.W["cls.b"],
                  out_mode=ops.OUT_STORE_F32, tile_n=128)
         self._conv(ws["hl"], "off.conv", ws["c"], B, T, d, 3, 1, a_row_stride=2 * d, act=ops.ACT_GELU)
-        ops.rowdot_sigmoid(ws["c"], self.W["off.w"], self.W["off.b"], ws["offsets"])
-        return ws["logits"][:, :, :self.L], ws["offsets"]
+        ops.rowdot_sigmoid(ws["c"], self.W["off.w"], self.W["off.b"], offsets)
+        return logits[:, :, :self.L], offsets
 
     def _lang_proj(self, a, a_row_stride, lang_id, ws, B, T, to_f16=False):
         """REF/model.py:176-180 folded: x = W_h h + (W_e emb[lang] + b), one bias row per batch item.  The result feeds
