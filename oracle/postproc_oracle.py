@@ -12,7 +12,6 @@ Parity pin: the reference ships no tests.  This restatemen
 
 Every function cites the reference lines it restates (REF = usamireko/WFL-ASR).
 """
-import math
 
 import numpy as np
 

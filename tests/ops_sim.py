@@ -30,9 +30,20 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
          m_rows=None, out_row_stride=None, out_batch_stride=0, bias=None, bias_batch_stride=0, act=ACT_NONE,
          out_mode=OUT_STORE_F16, alpha=1.0, tile_n=0, groups=1, a_col_group_stride=0, out_col_group_stride=0):
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and slab_k % 64 == 0 and n % 8 == 0
-    assert groups in (0, 1), "grouped contraction is not modelled"
-    assert w.shape == (n, len(shifts) * slab_k), (tuple(w.shape), n, len(shifts), slab_k)
     m_rows = a_rows if m_rows is None else m_rows
+    if groups > 1:  # Conv1d(groups=G): group g = A columns + g * stride, W rows / bias [g*n, (g+1)*n), output columns + g * stride
+        assert out_mode != OUT_GLU_F16 and not bias_batch_stride and w.shape[0] == groups * n
+        for g in range(groups):
+            og = torch.as_strided(out, (out.numel() - g * out_col_group_stride,), (1,),
+                                  out.storage_offset() + g * out_col_group_stride)
+            gemm(a, w[g * n:(g + 1) * n], og, n=n, slab_k=slab_k, shifts=shifts,
+                 cols=[c + g * a_col_group_stride for c in cols], a_rows=a_rows, a_cols=a_cols,
+                 a_row_stride=a_row_stride, a_batch_stride=a_batch_stride, batches=batches, m_rows=m_rows,
+                 out_row_stride=out_row_stride, out_batch_stride=out_batch_stride,
+                 bias=None if bias is None else bias[g * n:(g + 1) * n], act=act, out_mode=out_mode, alpha=alpha,
+                 tile_n=tile_n)
+        return
+    assert w.shape == (n, len(shifts) * slab_k), (tuple(w.shape), n, len(shifts), slab_k)
     av = _strided(a, (batches, a_rows, a_cols), (a_batch_stride, a_row_stride, 1)).float()
     wf = w.float()
     acc = torch.zeros(batches, m_rows, n)
@@ -72,11 +83,16 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
 
 
 def attention(qkv, out, *, B, T, H, hd, scale, q_col, k_col, v_col, rel_bias=None, gate=None):
-    assert qkv.dtype == torch.float16 and out.dtype == torch.float16 and rel_bias is None and gate is None
+    assert qkv.dtype == torch.float16 and out.dtype == torch.float16 and (rel_bias is None) == (gate is None)
     assert hd in (64, 256, 384, 512, 640), f"head_dim {hd} is not a built instantiation"
+    assert rel_bias is None or hd == 64, "the gated relative-position bias is built for head_dim 64 only"
     x = qkv.float()
     parts = [x[:, :, c:c + H * hd].view(B, T, H, hd).transpose(1, 2) for c in (q_col, k_col, v_col)]
-    p = torch.softmax(parts[0] @ parts[1].transpose(-1, -2) * scale, dim=-1)
+    scores = parts[0] @ parts[1].transpose(-1, -2) * scale
+    if rel_bias is not None:  # gate[b,h,q] * rel_bias[h, k - q + T - 1]
+        idx = torch.arange(T)[None, :] - torch.arange(T)[:, None] + T - 1
+        scores = scores + gate.view(B, H, T, 1) * rel_bias[:, idx].unsqueeze(0)
+    p = torch.softmax(scores, dim=-1)
     out.copy_((p @ parts[2]).transpose(1, 2).reshape(B, T, H * hd).half())
 
 
@@ -144,6 +160,28 @@ def gather_cols(src, dst, groups, w_in, w_out):
     dst.view(-1)[:rows * groups * w_out].view(rows, groups, w_out).copy_(src.view(rows, groups, w_in)[:, :, :w_out])
 
 
+def wavlm_conv0(wave, n_samples, w, gamma, beta, norm_mode, out, out_batch_stride, scratch):
+    """Conv1d(1, 512, k10, s5, no bias) + {0: GroupNorm(512, 512) over time | 1: input normalisation + LayerNorm} + GELU."""
+    x = wave[:, :n_samples].float()
+    if norm_mode == 1:
+        x = (x - x.mean(dim=1, keepdim=True)) / torch.sqrt(x.var(dim=1, keepdim=True, unbiased=False) + 1e-7)
+    y = F.conv1d(x[:, None], w[:, None, :], stride=5)  # [B, 512, T0]
+    if norm_mode == 0:
+        y = F.group_norm(y, 512, gamma, beta, 1e-5)
+    else:
+        y = F.layer_norm(y.transpose(1, 2), (512,), gamma, beta, 1e-5).transpose(1, 2)
+    y = F.gelu(y).transpose(1, 2)  # [B, T0, 512]
+    B, T0, _ = y.shape
+    _strided(out, (B, T0, 512), (out_batch_stride, 512, 1)).copy_(y.half())
+
+
+def wavlm_gate(x_f16, row_stride, B, T, H, hd, gw, gb, gconst, gate):
+    x = _strided(x_f16, (B * T, H, hd), (row_stride, hd, 1)).float()
+    proj = (x @ gw.T + gb).view(B, T, H, 2, 4).sum(-1)
+    ga, gb_ = torch.sigmoid(proj).unbind(-1)
+    gate.copy_((ga * (gb_ * gconst.view(1, 1, H) - 1.0) + 2.0).permute(0, 2, 1))
+
+
 def mel_power_frames(n_samples, hop):
     return 1 + n_samples // hop
 
@@ -184,6 +222,7 @@ def install(monkeypatch):
     """Routes ``wfl_asr_b200.ops`` through this module and lets the engine accept CPU tensors (tests only)."""
     from wfl_asr_b200 import engine, ops
     for name in ("gemm", "attention", "layernorm", "split_f16", "broadcast_rows", "rowdot_sigmoid", "lstm_layer",
-                 "gather_cols", "mel_power", "mel_power_scratch", "mel_power_frames", "logmel_scratch", "whisper_logmel"):
+                 "gather_cols", "mel_power", "mel_power_scratch", "mel_power_frames", "logmel_scratch", "whisper_logmel",
+                 "wavlm_conv0", "wavlm_gate"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(engine.Engine, "_require_device", lambda self, wave: None)

@@ -88,6 +88,18 @@ def test_whisper_engine_through_the_simulator(monkeypatch):
     _check(logits, offsets, ref_l, ref_o)
 
 
+@pytest.mark.parametrize("name", ["wavlm_base_plus", "wavlm_large"])
+def test_wavlm_engine_through_the_simulator(monkeypatch, name):
+    """WavLM packing on the CPU: conv stack as paired-row stride-2 GEMMs, GroupNorm / LayerNorm variants, weight-norm
+    fold, the positional conv as one grouped contraction (d/16 = 48 or 64 channels per group), gated relative-position
+    bias tables, post-LN (base-plus) and pre-LN (large) layer orders."""
+    cfg, labels, sd, wave, lang = mfg.case_inputs(name)
+    wave, lang = wave[:1], lang[:1]
+    eng, logits, offsets = _run(monkeypatch, cfg, sd, labels, wave, lang)
+    ref_l, ref_o = to.forward(wave, sd, cfg, lang)
+    _check(logits, offsets, ref_l, ref_o)
+
+
 def test_sub_batched_forward_layout(monkeypatch):
     """WFL_SUB_BATCH: the batch in equal parts writing straight into the full-size outputs (bitwise equality with the
     single pass is a property of the real kernels and is asserted on the GPU; here: same values, right slices)."""

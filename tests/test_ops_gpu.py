@@ -1,6 +1,5 @@
 """GPU (-m gpu): every C-ABI op against a plain torch fp32 statement of the same op / the oracle.
 All calls go through wfl_asr_b200.ops -> ctypes -> libwfl_b200.so."""
-import math
 
 import numpy as np
 import pytest
