@@ -100,6 +100,22 @@ def test_wavlm_engine_through_the_simulator(monkeypatch, name):
     _check(logits, offsets, ref_l, ref_o)
 
 
+@pytest.mark.parametrize("name,use_lang,mll", [("wavlm_base_plus", True, 80), ("wavlm_base_plus", False, 120),
+                                                ("wavlm_large", True, 90), ("whisper_base_full", False, 1400)])
+def test_max_label_len_paths(monkeypatch, name, use_lang, mll):
+    """REF/model.py:166-174 (the batched training/eval caller fixes T to the label length): hidden states truncated or
+    zero-padded AFTER the encoder's final LayerNorm, for encoders with and without a final norm, with and without the
+    language projection, into the BiLSTM or straight into the Conformer."""
+    cfg, labels, sd, wave, lang = mfg.case_inputs(name)
+    wave, lang = wave[:1], (lang[:1] if use_lang else None)
+    ops_sim.install(monkeypatch)
+    eng = Engine(sd, cfg, len(labels), CPU)
+    lg, of = eng.forward(wave, lang, max_label_len=mll)
+    ref_l, ref_o = to.forward(wave, sd, cfg, lang, max_label_len=mll)
+    assert lg.shape == ref_l.shape and lg.shape[1] == mll
+    _check(lg.clone(), of.clone(), ref_l, ref_o)
+
+
 def test_sub_batched_forward_layout(monkeypatch):
     """WFL_SUB_BATCH: the batch in equal parts writing straight into the full-size outputs (bitwise equality with the
     single pass is a property of the real kernels and is asserted on the GPU; here: same values, right slices)."""

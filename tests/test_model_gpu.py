@@ -100,6 +100,23 @@ def test_language_mean_fast_path(name):
     assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
 
 
+@pytest.mark.parametrize("name,use_lang,mll", [("wavlm_base_plus", True, 80), ("wavlm_base_plus", False, 120),
+                                                ("wavlm_large", True, 90), ("whisper_base_full", False, 1400),
+                                                ("whisper_base_full", True, 1600), ("mel_none_full", True, 90)])
+def test_max_label_len(name, use_lang, mll):
+    """REF/model.py:166-174: the batched training/eval caller (REF/train.py:485-495) fixes T to the label length --
+    hidden states truncated or zero-padded after the encoder, before lang_proj / BiLSTM / Conformer."""
+    if name not in SUPPORTED:
+        pytest.skip("case filtered out")
+    cfg, labels, sd, wave, lang, model = _build(name)
+    lang_d = lang.to(DEV) if use_lang else None
+    logits, offsets = model(wave.to(DEV), lang_d, max_label_len=mll)
+    ref_l, ref_o = to.forward(wave, sd, cfg, lang if use_lang else None, max_label_len=mll)
+    assert tuple(logits.shape) == tuple(ref_l.shape) and logits.shape[1] == mll
+    rel, agree, agree_safe, off_err = _compare(f"{name}/mll{mll}", logits.float().cpu(), offsets.float().cpu(), ref_l, ref_o)
+    assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
+
+
 def test_sub_batched_forward_is_bitwise_identical(monkeypatch):
     """engine.forward may push a large batch through in equal sub-batches (L2-resident working set, DESIGN.md section 3);
     clips are independent and the kernels batch-invariant, so the result must equal the single pass bit for bit."""
