@@ -128,3 +128,24 @@ def test_wav_reader(tmp_path):
         f.write(b"data" + struct.pack("<I", x.nbytes) + x.tobytes())
     audio, sr = _read_wav(str(p))
     assert sr == 16000 and np.array_equal(audio, x.astype(np.float64) / 32768.0)
+
+
+def test_cli_flags_and_error_paths(tmp_path):
+    """python -m wfl_asr_b200.infer: the reference's flags (REF/infer.py:362-373), its sampling-flag validation
+    messages with exit status 1 (REF/infer.py:377-392), and -- on a box without a GPU -- a loud refusal, not a CPU run."""
+    from click.testing import CliRunner
+    from wfl_asr_b200 import infer
+    cmd = infer.cli_command()
+    flags = {o for p in cmd.params for o in p.opts}
+    assert {"--checkpoint", "-ckpt", "--config", "-c", "--output", "-o", "--lang-id", "-l", "--sample", "-s", "--top-k", "-tk",
+            "--top-p", "-tp", "--temperature", "-temp", "--device", "-d", "--confidence-threshold", "-ct"} <= flags
+    base = ["clip.wav", "-ckpt", "m.pt", "-c", "config.yaml"]
+    run = CliRunner().invoke
+    for extra, msg in ((["-s"], "neither --top-k nor --top-p"), (["-s", "-tk", "3", "-tp", "0.5"], "both --top-k and --top-p"),
+                       (["-s", "-tp", "1.5"], "top-p must be between"), (["-s", "-tk", "3", "-temp", "0"], "temperature must be")):
+        r = run(cmd, base + extra)
+        assert r.exit_code == 1 and msg in r.output, (extra, r.output)
+    assert run(cmd, ["clip.wav"]).exit_code == 2  # click: missing required --checkpoint / --config
+    if not torch.cuda.is_available():
+        r = run(cmd, base)
+        assert r.exit_code == 1 and "no CPU path" in r.output

@@ -367,7 +367,8 @@ def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_
     return results
 
 
-def _cli():
+def cli_command():
+    """The click command behind ``python -m wfl_asr_b200.infer`` (same flags as REF/infer.py:362-373)."""
     import click
     from pathlib import Path
 
@@ -428,7 +429,11 @@ def _cli():
             for start, end, ph in segments:
                 print(f"({round(start, 2)}, {round(end, 2)}, {ph})")
 
-    main()
+    return main
+
+
+def _cli():
+    cli_command()()
 
 
 if __name__ == "__main__":
