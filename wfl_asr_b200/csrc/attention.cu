@@ -278,11 +278,16 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     float l_sum = 0.f;  // this warp's 32 columns only; the two halves are added in the epilogue
     constexpr int kOHalf = HD / 2;
 
-    for (int j = 0; j < n_kv; ++j) {
+    // S buffer j % S_BUFS and its phase (j / S_BUFS) & 1 as running counters in the plain kernel (S_BUFS = 3 costs a
+    // multiply-high per tile otherwise); the bias kernel has no registers to spare for them and recomputes
+    int ss_run = 0;
+    uint32_t ph_run = 0;
+    for (int j = 0; j < n_kv; ++j, ss_run = (ss_run + 1 == S_BUFS ? 0 : ss_run + 1), ph_run ^= (ss_run == 0)) {
       const int sb = j & 1;         // P / exchange buffer parity
-      const int ss = j % S_BUFS;    // S buffer
+      const int ss = kHasBias ? j % S_BUFS : ss_run;
+      const uint32_t ss_phase = kHasBias ? static_cast<uint32_t>((j / S_BUFS) & 1) : ph_run;
       const int kv0 = j * KV_TILE + ch * 32;  // first key of this warp's columns
-      mbar_wait(&s_full[ss], (j / S_BUFS) & 1);
+      mbar_wait(&s_full[ss], ss_phase);
       tc_fence_after();
 #ifndef WFL_EXP_NOSOFTMAX  // experiment build only: skip the math, keep the barrier protocol
       uint32_t v[32];
@@ -352,15 +357,26 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // P = 2^(x - m_used) -> f16 -> swizzled smem; row sum in fp32
         const float neg_m = -m_used;
         const uint64_t sc2 = pk2(sc, sc), negm2 = pk2(neg_m, neg_m);
+        // row sum: packed accumulators (FADD2, 16 adds for 32 columns) in the plain kernel; the bias kernel is at its
+        // register limit and keeps four scalar partial sums (the packed form spills there)
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
+        uint64_t sum2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float a0, a1;
           upk2(fma2(pk2u(v[i], v[i + 1]), sc2, negm2), a0, a1);  // one FFMA2 for the pair
           const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
-          sum[(i >> 1) & 3] += e0 + e1;
+          if constexpr (kBias) {
+            sum[(i >> 1) & 3] += e0 + e1;
+          } else {
+            sum2[(i >> 1) & 1] = add2(sum2[(i >> 1) & 1], pk2(e0, e1));
+          }
           pk[i >> 1] = pack_f16(e0, e1);
+        }
+        if constexpr (!kBias) {
+          upk2(sum2[0], sum[0], sum[1]);
+          upk2(sum2[1], sum[2], sum[3]);
         }
         if constexpr (kPTmem) {
           // this warp's 32 keys = 16 packed columns of the P tile that overlays S buffer ss (both warps of the pair
