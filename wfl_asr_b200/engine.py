@@ -2,7 +2,7 @@
 sequence of libwfl_b200.so launches on the caller's CUDA stream.
 
 Data layout in HBM (B clips, T frames, d hidden), all row-major with channels last:
-  x      fp32 [B, T, d]   residual stream (GEMM epilogues accumulate into it with TMA reduce-add)
+  x      fp32 [B, T, d]   residual stream (GEMM epilogues accumulate into it with red.global.add.v4.f32)
   h, ctx f16 [B*T, d]    LayerNorm outputs / attention context  (GEMM A operands)
   qkv    f16 [B*T, 3d]   packed projections, read in place by the attention kernel
   u      f16 [B*T, F]    MLP / GLU intermediates
