@@ -50,6 +50,21 @@ def test_mel_filters_match_transformers():
         assert np.abs(to.slaney_mel_filters(n_mels) - ref.astype(np.float32)).max() <= 1e-7
 
 
+def test_htk_filters_and_mel_power_match_torchaudio():
+    """encoder_type "none" (REF/model.py:85-90): the oracle's restated filter bank / MelSpectrogram against torchaudio."""
+    ta = pytest.importorskip("torchaudio")
+    from wfl_asr_b200.frontend import htk_mel_filters
+    for n_mels in (64, 80, 128):
+        ref = ta.functional.melscale_fbanks(201, 0.0, 8000.0, n_mels, 16000, norm=None, mel_scale="htk")
+        assert torch.equal(to.htk_mel_filters(n_mels), ref) and torch.equal(htk_mel_filters(n_mels), ref)
+    ms = ta.transforms.MelSpectrogram(sample_rate=16000, n_fft=400, hop_length=320, n_mels=80)
+    wave = torch.stack([torch.from_numpy(to.synth_wave(5 + i, 1.03)).float() for i in range(2)])
+    ref = ms(wave).transpose(1, 2)
+    got = to.mel_power(wave, ms.spectrogram.window, ms.mel_scale.fb, 320)
+    assert got.shape == ref.shape == (2, 1 + wave.shape[1] // 320, 80)
+    assert (got - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+
+
 def test_wavlm_frame_count():
     assert to.wavlm_num_frames(160000) == 499
     assert to.wavlm_num_frames(480000) == 1499
