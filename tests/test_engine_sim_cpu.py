@@ -116,6 +116,19 @@ def test_max_label_len_paths(monkeypatch, name, use_lang, mll):
     _check(lg.clone(), of.clone(), ref_l, ref_o)
 
 
+def test_conformer_head_dim_padded_to_a_built_size(monkeypatch):
+    """conformer_heads 6 at d = 768 gives head_dim 128, which the attention kernels are not built for: the engine pads
+    every head's q/k/v rows and out_proj columns to 256 (scale stays 1/sqrt(128))."""
+    cfg, labels, sd, wave, lang = mfg.case_inputs("wavlm_base_plus")
+    cfg = copy.deepcopy(cfg)
+    cfg["model"]["conformer_heads"] = 6
+    wave, lang = wave[:1], lang[:1]
+    eng, logits, offsets = _run(monkeypatch, cfg, sd, labels, wave, lang)
+    assert eng.conf_hdp == 256 and eng.conf_aw == 6 * 256
+    ref_l, ref_o = to.forward(wave, sd, cfg, lang)
+    _check(logits, offsets, ref_l, ref_o)
+
+
 def test_sub_batched_forward_layout(monkeypatch):
     """WFL_SUB_BATCH: the batch in equal parts writing straight into the full-size outputs (bitwise equality with the
     single pass is a property of the real kernels and is asserted on the GPU; here: same values, right slices)."""

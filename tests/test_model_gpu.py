@@ -117,6 +117,27 @@ def test_max_label_len(name, use_lang, mll):
     assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
 
 
+@pytest.mark.parametrize("name,heads", [("wavlm_base_plus", 6), ("whisper_base_cfg2", 4)])
+def test_conformer_head_dim_128_runs_padded(name, heads):
+    """Head dims the attention kernels are not built for (128: conformer_heads 4 at d 512, the reference's default
+    head count; 6 at d 768) run with every head zero-padded to the next built size (256) -- same numbers, same bar."""
+    if name not in SUPPORTED:
+        pytest.skip("case filtered out")
+    import copy
+    cfg, labels, _, wave, lang = mfg.case_inputs(name)
+    cfg = copy.deepcopy(cfg)
+    cfg["model"]["conformer_heads"] = heads
+    sd = to.random_state_dict(cfg, len(labels), seed=31)
+    model = BIOPhonemeTagger(cfg, labels)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    logits, offsets = model(wave.to(DEV), lang.to(DEV))
+    assert model.engine().conf_hdp == 256
+    ref_l, ref_o = to.forward(wave, sd, cfg, lang)
+    rel, agree, agree_safe, off_err = _compare(f"{name}/heads{heads}", logits.float().cpu(), offsets.float().cpu(), ref_l, ref_o)
+    assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
+
+
 def test_sub_batched_forward_is_bitwise_identical(monkeypatch):
     """engine.forward may push a large batch through in equal sub-batches (L2-resident working set, DESIGN.md section 3);
     clips are independent and the kernels batch-invariant, so the result must equal the single pass bit for bit."""
