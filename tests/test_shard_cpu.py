@@ -77,3 +77,13 @@ def test_gather_single_process():
     rec["ph"] = [1, 2, 3]
     out = shard.gather_segments([(7, rec), (9, rec[:0])], torch.device("cpu"))
     assert list(out[7]["ph"]) == [1, 2, 3] and len(out[9]) == 0
+
+
+def test_frames_for_every_encoder_type():
+    """Frame counts the sharding cost model and the per-utterance decode lengths use: Whisper pads to 30 s, WavLM's
+    conv chain (TF/models/wavlm: k 10,3,3,3,3,2,2 / s 5,2,2,2,2,2,2), the centred STFT of encoder_type "none"."""
+    assert shard.frames_for(16000, "whisper") == 1500 and shard.frames_for(480000, "whisper") == 1500
+    assert shard.frames_for(160000, "wavlm") == 499 and shard.frames_for(480000, "wavlm") == 1499
+    assert shard.frames_for(399, "wavlm") == 0
+    assert shard.frames_for(32000, "none") == 101 and shard.frames_for(480000, "none") == 1501
+    assert shard.frames_for(32000, "none", hop=160) == 201
