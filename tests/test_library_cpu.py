@@ -149,3 +149,23 @@ def test_cli_flags_and_error_paths(tmp_path):
     if not torch.cuda.is_available():
         r = run(cmd, base)
         assert r.exit_code == 1 and "no CPU path" in r.output
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm the driver times beside the GPU arm): runs without a GPU, prints ONE JSON
+    line with the contract's keys, same metric/unit as the GPU arm, e2e == value, zero transfer bytes."""
+    import json
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample-clips", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "audio_seconds_labeled_per_second" and d["unit"] == "audio-s/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
+    assert "workload" in d["config"]
