@@ -36,11 +36,21 @@ CASES = {
     "whisper_base_full": (dict(), 2, 2, 3.0, 11),
     "whisper_base_cfg2": (dict(enable_bilstm=False, enable_dilated_conv=False, num_conformer_layers=4), 2, 1, 2.0, 12),
     "wavlm_base_plus": (dict(encoder_type="wavlm", enable_bilstm=False, enable_dilated_conv=False), 2, 2, 2.0, 13),
-    # conformer_heads=4 -> head_dim 256 (heads=2 at d=1024 needs the head_dim-512 attention variant, not built yet)
+    # conformer_heads=4 -> head_dim 256 at d=1024, with the dilated stack
     "wavlm_large": (dict(encoder_type="wavlm", wavlm_model="microsoft/wavlm-large", num_conformer_layers=1,
                          conformer_heads=4, enable_bilstm=False), 2, 2, 1.5, 14),
     # encoder_type "none" (REF/model.py:82-91): MelSpectrogram power features, hidden size 80, 101 frames per 2 s
     "mel_none_full": (dict(encoder_type="none"), 0, 2, 2.0, 15),
+    # --- the BASELINE.json config SHAPES (encoder depth cut to 2 layers so the fixtures and the CPU oracle stay small) ---
+    # configs[0]: WavLM-base-plus + 2 Conformer (config.yaml heads 2 -> head dim 384), batch 1 x 10 s -> T = 499
+    "cfg1_wavlm_base_plus_10s": (dict(encoder_type="wavlm", enable_bilstm=False, enable_dilated_conv=False,
+                                      num_conformer_layers=2), 2, 1, 10.0, 16),
+    # configs[3]: WavLM-large + Conformer with heads 2 -> head dim 512 (attention_big_kernel<512>), d = 1024 packing
+    "cfg4_wavlm_large_hd512": (dict(encoder_type="wavlm", wavlm_model="microsoft/wavlm-large", enable_bilstm=False,
+                                    enable_dilated_conv=False, num_conformer_layers=2), 2, 2, 2.5, 17),
+    # configs[4]: Whisper-large-v3 (d 1280, 20 heads, 128 mels) + BiLSTM(2) H 640 + Conformer heads 2 -> head dim 640
+    # (attention_big_kernel<640>, lstm_kernel<640,16,8>) + dilated stack
+    "cfg5_whisper_large_v3_full": (dict(whisper_model="openai/whisper-large-v3", num_conformer_layers=2), 2, 1, 3.0, 18),
 }
 
 

@@ -169,3 +169,28 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 == d["e2e"]["d2h_bytes_per_step"]
     assert "workload" in d["config"]
+
+
+def test_model_rejects_shapes_the_reference_cannot_run():
+    """d % conformer_heads != 0 fails in the reference's nn.MultiheadAttention (REF/model.py:26); even conv kernel
+    sizes change the reference's frame alignment / length (REF/model.py:33,46-49,126-133) and are not built."""
+    import copy
+
+    import pytest
+
+    from wfl_asr_b200 import synth
+    from wfl_asr_b200.model import BIOPhonemeTagger
+    labels = synth.synth_labels(4)
+    base = synth.workload_config("cfg2")
+    base["model"]["encoder_layers_override"] = 1
+    for key, val in (("conformer_heads", 3), ("conformer_kernel_size", 30)):
+        cfg = copy.deepcopy(base)
+        cfg["model"][key] = val
+        with pytest.raises(ValueError):
+            BIOPhonemeTagger(cfg, labels)
+    cfg = copy.deepcopy(base)
+    cfg["model"].update(enable_dilated_conv=True, dilated_conv_kernel=4)
+    with pytest.raises(ValueError):
+        BIOPhonemeTagger(cfg, labels)
+    cfg["model"].update(enable_dilated_conv=False)  # an unused even kernel is not an error
+    BIOPhonemeTagger(cfg, labels)

@@ -25,6 +25,7 @@ from wfl_asr_b200.model import BIOPhonemeTagger  # noqa: E402
 from wfl_asr_b200.pipeline import Labeler  # noqa: E402
 
 DEV = torch.device("cuda:0")
+NORTH_STAR_TAG_AGREEMENT = 0.999  # BASELINE.json north_star: frame tag agreement >= 99.9 % (asserted on full-size clips)
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "forward_golden.npz"))
 _SEL = [s for s in os.environ.get("WFL_TEST_CASES", "").split(",") if s]
 SUPPORTED = [n for n in mfg.CASES if not _SEL or any(s in n for s in _SEL)]
@@ -66,7 +67,9 @@ def test_forward_matches_oracle(name):
     # leaves room for one or two near-tie frames at these small test sizes)
     assert rel <= 2e-3, f"logit error {rel} above the fp16 bar 2e-3 (north_star tolerance 1e-2)"
     assert agree_safe == 1.0
-    assert agree >= 0.998
+    # north_star bar 99.9 %; a fixture with fewer than 1000 frames may lose at most one near-tie frame
+    frames = ref_l.shape[0] * ref_l.shape[1]
+    assert agree >= min(NORTH_STAR_TAG_AGREEMENT, 1.0 - 1.0 / frames) - 1e-9
     assert off_err <= 2e-3
 
 
@@ -195,6 +198,50 @@ def test_pipeline_lab_bit_exact_given_gpu_logits(median_k, mode, thr):
     assert mismatched_frames <= 2  # softmax rounding may flip a frame that sits exactly on the threshold
 
 
+class _LabelStub(torch.nn.Module):
+    """What pipeline.Labeler needs from a model when only post-processing runs: the label tables and a device."""
+
+    def __init__(self, labels):
+        super().__init__()
+        self.label_list = list(labels)
+        self.label2id = {t: i for i, t in enumerate(labels)}
+        self.id2label = dict(enumerate(labels))
+        self.anchor = torch.nn.Parameter(torch.zeros(1))
+
+
+def test_canonical_to_lang_remap_and_merge_golden():
+    """REF/infer.py:303-310: decoded segments are renamed through phoneme_merge_map.json for the requested language and
+    THEN merged, so two different model phonemes that map to one output name merge.  Here the remap is the ph_class
+    table of wfl_merge_segments (pipeline.Labeler.set_output_names); segments and .lab text must equal what the
+    reference's decode_bio_tags -> canonical_to_lang -> merge_adjacent_segments -> save_lab produced
+    (tests/golden/align_golden.json.gz, reference-generated)."""
+    import gzip
+    import json
+    from wfl_asr_b200 import utils
+    with gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "align_golden.json.gz"), "rt") as f:
+        gold = json.load(f)
+    labels, mm = gold["labels"], gold["merge_map"]
+    stub = _LabelStub(labels).to(DEV)
+    merged_two = 0
+    for rec in gold["remap"]:
+        T = len(rec["tags"])
+        ids = torch.tensor([labels.index(t) for t in rec["tags"]])
+        logits = torch.nn.functional.one_hot(ids, len(labels)).float()[None].mul(12.0).to(DEV)
+        offsets = torch.tensor(rec["offsets"], dtype=torch.float32)[None].to(DEV)
+        for mode in ("right", "left", "previous", "none"):
+            lab = Labeler(stub, median_filter=1, merge_mode=mode, confidence_threshold=0.0)
+            lab.set_output_names([utils.canonical_to_lang(p, rec["lang"], mm) for p in lab.phon])
+            _, merged, nout, fcb, n_files = lab.postprocess(logits, offsets)
+            got = lab.fetch(merged, nout, fcb, n_files, T)[0]
+            want = [tuple(r) for r in rec["merged"][mode]]
+            assert got == want, (rec["lang"], mode, T)
+            assert utils.htk_lines(got) == rec["lab"][mode]
+        plain = Labeler(stub, median_filter=1, merge_mode="right", confidence_threshold=0.0)
+        _, merged, nout, fcb, n_files = plain.postprocess(logits, offsets)
+        merged_two += len(plain.fetch(merged, nout, fcb, n_files, T)[0]) > len(rec["merged"]["right"])
+    assert merged_two >= 5  # the remap really merged segments that stay apart without it
+
+
 def test_utils_dropins_match_oracle(golden):
     from wfl_asr_b200 import utils
     for rec in golden["decode"][:12]:
@@ -232,6 +279,44 @@ def test_graph_replay_matches_direct_launches():
         lt = torch.tensor((lg * n)[:n], device=DEV)
         assert graphed.label_host(batch, lt) == direct.label_host(batch, lt)
     assert len(graphed._graphs) == 1 and not direct._graphs
+
+
+def test_graph_replay_survives_workspace_eviction():
+    """The engine / labeler workspace caches keep one shape each.  Alternating two shapes through label_host must not
+    let a replayed graph touch the evicted (freed) workspaces of its shape: each captured pass owns references to
+    what it captured.  Shapes A, B, A, B ... with graphs on must equal direct launches, also with allocator churn
+    between the calls (so freed blocks would be handed out again if the graph did not hold them)."""
+    cfg, labels, sd, wave, lang, model = _build("wavlm_base_plus")
+    direct = Labeler(model, median_filter=3, merge_mode="right", confidence_threshold=0.1, use_graphs=False)
+    graphed = Labeler(model, median_filter=3, merge_mode="right", confidence_threshold=0.1, use_graphs=True)
+    a = wave.clone().pin_memory()                       # [2, 32000]
+    b = torch.cat([wave, wave.flip(0)], 0)[:3, :24000].contiguous().pin_memory()  # other batch size AND length
+    la, lb = torch.tensor([0, 1], device=DEV), torch.tensor([1, 0, 1], device=DEV)
+    want_a, want_b = direct.label_host(a, la), direct.label_host(b, lb)
+    junk = []
+    for r in range(3):
+        assert graphed.label_host(a, la) == want_a, f"round {r}: shape A differs after shape B evicted its workspaces"
+        junk.append(torch.randn(1 << 22, device=DEV))  # churn: reuse whatever the caches freed
+        assert graphed.label_host(b, lb) == want_b, f"round {r}: shape B differs"
+        junk.append(torch.randn(1 << 22, device=DEV))
+    assert len(graphed._graphs) == 2
+
+
+def test_forward_returns_fresh_tensors():
+    """REF/infer.py:268-275 keeps one logits tensor per language and averages afterwards: ``forward`` must return
+    tensors that a later forward does not overwrite (the engine's workspace views stay internal)."""
+    cfg, labels, sd, wave, lang, model = _build("whisper_base_cfg2")
+    x = wave.to(DEV)
+    B = x.shape[0]
+    l0, o0 = model(x, torch.zeros(B, dtype=torch.long, device=DEV))
+    keep_l, keep_o = l0.clone(), o0.clone()
+    l1, o1 = model(x, torch.ones(B, dtype=torch.long, device=DEV))
+    assert l0.is_contiguous() and l0.data_ptr() != l1.data_ptr()
+    assert torch.equal(l0, keep_l) and torch.equal(o0, keep_o)
+    assert not torch.equal(l0, l1)  # the two languages really differ
+    mean = torch.stack([l0, l1]).mean(dim=0)
+    lm, _ = model.forward_language_mean(x, [0, 1])
+    assert torch.equal(mean, lm)
 
 
 def _write_wav(path, x, sr=16000):
@@ -346,10 +431,9 @@ def test_bulk_label_corpus_ragged(name, bucket):
                             max_clips=3, bucket_samples=bucket)
     assert len(got) == len(waves)
     etype = cfg["model"]["encoder_type"]
-    plan = shard.plan_shards(lens, 1, etype)[0]
     bsz = 480000 if etype == "whisper" else bucket
     seen = 0
-    for padded, group in shard.bucket_batches(plan, lens, 3, 32 * 480000, bsz):
+    for padded, group in shard.plan_batches(lens, 1, etype, 3, 32 * 480000, bsz)[0]:
         host = torch.zeros(len(group), padded)
         for j, i in enumerate(group):
             host[j, :lens[i]] = torch.from_numpy(waves[i])
@@ -392,7 +476,7 @@ def test_full_size_cfg2_properties():
         assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch 32 and batch 1"
     ref_l, ref_o = to.forward(wave[13:14], sd, cfg, lang[13:14].cpu())
     rel, agree, agree_safe, off_err = _compare("cfg2 full size, clip 13", l1[13:14].float().cpu(), o1[13:14].float().cpu(), ref_l, ref_o)
-    assert rel <= 2e-3 and agree_safe == 1.0
+    assert rel <= 2e-3 and agree_safe == 1.0 and agree >= NORTH_STAR_TAG_AGREEMENT
     lab = Labeler(model, median_filter=5, merge_mode="right", confidence_threshold=0.5)
     ids, merged, nout, fcb, n_files = lab.postprocess(l1, o1)
     segs = lab.fetch(merged, nout, fcb, n_files, 1500)
@@ -427,7 +511,63 @@ def test_full_size_cfg3_properties():
         assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch 64 and batch 1"
     ref_l, ref_o = to.forward(wave[41:42], sd, cfg, lang[41:42].cpu())
     rel, agree, agree_safe, off_err = _compare("cfg3 full size, clip 41", l1[41:42].float().cpu(), o1[41:42].float().cpu(), ref_l, ref_o)
-    assert rel <= 2e-3 and agree_safe == 1.0 and agree >= 0.998
+    assert rel <= 2e-3 and agree_safe == 1.0 and agree >= NORTH_STAR_TAG_AGREEMENT
+
+
+def _full_size(workload, B, seconds, probe, check_clip, seed0):
+    """Full-depth model of a BASELINE config on B clips: run-to-run determinism, batch invariance of the probed clips
+    (bitwise), and the fp32 oracle on one clip at the north_star bars (1e-2 logits -- held to 2e-3 --, >= 99.9 % tags)."""
+    from wfl_asr_b200 import synth
+    cfg = synth.workload_config(workload)
+    labels = synth.synth_labels(30)
+    model = synth.bench_model(BIOPhonemeTagger, cfg, labels)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    base = [synth.synth_wave(seed0 + i, seconds) for i in range(min(B, 4))]
+    wave = torch.from_numpy(np.stack([base[i % len(base)] * (0.5 + 0.5 * ((i * 7) % 11) / 11.0) for i in range(B)]).astype(np.float32))
+    lang = torch.tensor([i % 2 for i in range(B)], device=DEV)
+    l1, o1 = (t.clone() for t in model(wave.to(DEV), lang))
+    l2, o2 = model(wave.to(DEV), lang)
+    assert torch.equal(l1, l2) and torch.equal(o1, o2), "forward is not deterministic"
+    for i in probe:
+        li, oi = model(wave[i:i + 1].to(DEV), lang[i:i + 1])
+        assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch {B} and batch 1"
+    c = check_clip
+    ref_l, ref_o = to.forward(wave[c:c + 1], sd, cfg, lang[c:c + 1].cpu())
+    rel, agree, agree_safe, off_err = _compare(f"{workload} full size, clip {c}", l1[c:c + 1].float().cpu(),
+                                               o1[c:c + 1].float().cpu(), ref_l, ref_o)
+    assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
+    assert agree >= NORTH_STAR_TAG_AGREEMENT
+    return model, labels, l1, o1
+
+
+def test_full_size_cfg1_properties():
+    """BASELINE configs[0] at full size: WavLM-base-plus (12 layers, GroupNorm front-end, post-LN) + 2 Conformer blocks
+    (heads 2 -> head dim 384), batch 1 x 10 s -> 499 frames; plus a batch of 3 to check batch invariance."""
+    model, labels, l1, o1 = _full_size("cfg1", 3, 10.0, probe=(0, 2), check_clip=2, seed0=500)
+    assert l1.shape[1] == 499
+    lab = Labeler(model, median_filter=5, merge_mode="right", confidence_threshold=0.5)
+    ids, merged, nout, fcb, n_files = lab.postprocess(l1, o1)
+    segs = lab.fetch(merged, nout, fcb, n_files, l1.shape[1])
+    for b in range(3):
+        want = po.merge_adjacent_segments(po.decode_bio_tags([labels[k] for k in ids[b].cpu().numpy()], 0.02,
+                                                             o1[b].float().cpu().numpy()), "right")
+        assert segs[b] == want
+
+
+def test_full_size_cfg4_properties():
+    """BASELINE configs[3] at full size: WavLM-large (24 pre-LN layers, LayerNorm front-end, input normalisation) + 6
+    Conformer blocks with heads 2 -> head dim 512 (attention_big_kernel<512>), d = 1024; 6 clips x 16 s (the corpus'
+    mean utterance length) -> 799 frames."""
+    model, labels, l1, o1 = _full_size("cfg4", 6, 16.0, probe=(0, 5), check_clip=3, seed0=520)
+    assert l1.shape[1] == 799 and model.engine().conf_hdp == 512
+
+
+def test_full_size_cfg5_properties():
+    """BASELINE configs[4] at full size: Whisper-large-v3 (32 layers, d 1280, 20 heads, 128 mels) + BiLSTM(2) with H 640
+    (lstm_kernel<640,16,8>) + 8 Conformer blocks with head dim 640 (attention_big_kernel<640>) + dilated stack."""
+    model, labels, l1, o1 = _full_size("cfg5", 4, 30.0, probe=(1,), check_clip=1, seed0=540)
+    assert l1.shape[1] == 1500 and model.engine().conf_hdp == 640 and model.engine().lstm_hp == 640
 
 
 def test_encoder_run_to_run_determinism_soak():

@@ -41,6 +41,27 @@ def test_bucket_batches_respect_caps():
     assert all(all(lens[i] == p for i in g) for p, g in exact)
 
 
+def test_plan_batches_is_world_size_independent_and_balanced():
+    """Batch-level sharding: the SET of batches does not depend on the world size (so results cannot either), every
+    utterance is in exactly one batch, and the LPT deal balances the ranks' estimated cost."""
+    lens = _lengths(3000)
+    one = shard.plan_batches(lens, 1, "wavlm", max_clips=16, max_samples_per_batch=16 * 480000)[0]
+    key = lambda b: (b[0], tuple(b[1]))
+    for world in (2, 4, 8):
+        plan = shard.plan_batches(lens, world, "wavlm", max_clips=16, max_samples_per_batch=16 * 480000)
+        assert plan == shard.plan_batches(lens, world, "wavlm", max_clips=16, max_samples_per_batch=16 * 480000)
+        flat = [b for r in plan for b in r]
+        assert sorted(map(key, flat)) == sorted(map(key, one))
+        assert sorted(i for _, g in flat for i in g) == list(range(len(lens)))
+        loads = [sum(shard.cost(shard.frames_for(p, "wavlm")) * len(g) for p, g in r) for r in plan]
+        assert max(loads) <= 1.03 * (sum(loads) / world)
+        # batches stay full: at most one partial batch per length bucket in the whole corpus, not one per rank
+        partial = sum(1 for p, g in flat if len(g) < min(16, 16 * 480000 // p))
+        assert partial <= len({p for p, _ in flat})
+    for p, g in one:
+        assert all(p - 8000 < lens[i] <= p for i in g)
+
+
 def _worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

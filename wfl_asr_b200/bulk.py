@@ -12,21 +12,68 @@ from . import shard
 from .pipeline import SEG_DTYPE, Labeler
 
 
+class _Stager:
+    """Pinned staging for a rank's batches: ``depth`` pinned buffers sized for the largest batch, filled by a small
+    thread pool (numpy row copies release the GIL) one batch ahead of the GPU.  Only the padding tail of each row is
+    zeroed -- the samples themselves are written exactly once."""
+
+    def __init__(self, batches, lens, waves, workers=4, depth=3):
+        from concurrent.futures import ThreadPoolExecutor
+        self.batches, self.lens, self.waves = batches, lens, waves
+        cap = max((len(g) * p for p, g in batches), default=0)
+        self.buffers = [torch.empty(cap, dtype=torch.float32).pin_memory() for _ in range(depth)] if cap else []
+        self.depth = depth
+        self.pool = ThreadPoolExecutor(max_workers=max(1, workers))
+        self.jobs = {}
+
+    def _fill_row(self, row, i):
+        n = self.lens[i]
+        row[:n] = np.asarray(self.waves[i], dtype=np.float32)
+        row[n:] = 0.0
+
+    def submit(self, k):
+        if k >= len(self.batches) or k in self.jobs:
+            return
+        padded, group = self.batches[k]
+        host = self.buffers[k % self.depth][:len(group) * padded].view(len(group), padded)
+        arr = host.numpy()
+        self.jobs[k] = (host, [self.pool.submit(self._fill_row, arr[j], i) for j, i in enumerate(group)])
+
+    def get(self, k):
+        host, futures = self.jobs.pop(k)
+        for f in futures:
+            f.result()
+        return host
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
 def label_corpus(model, waves, lang_ids=None, *, median_filter=1, merge_mode="right", confidence_threshold=0.0,
-                 max_clips=32, max_samples_per_batch=32 * 480000, bucket_samples=8000):
-    """waves: list of 1-D float32 numpy arrays (16 kHz, already peak-normalised, each <= 30 s).
-    Returns on rank 0 a list (per utterance) of [(start, end, phoneme)]; None on other ranks."""
+                 max_clips=32, max_samples_per_batch=32 * 480000, bucket_samples=8000, lengths=None,
+                 shard_by="batch", stage_workers=4, gather=True):
+    """waves: sequence of 1-D float32 arrays (16 kHz, already peak-normalised, each <= 30 s); only the utterances of
+    this rank's shard are ever indexed, so a lazily materialising sequence works when ``lengths`` (samples per
+    utterance) is given.  ``shard_by``: "batch" deals whole length-bucketed batches to ranks (shard.plan_batches),
+    "utterance" deals single utterances (shard.plan_shards).  Returns on rank 0 a list (per utterance) of
+    [(start, end, phoneme)]; None on other ranks.  The end-of-run gather is the only collective."""
     dev = next(model.parameters()).device
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    lens = [int(len(w)) for w in waves]
+    lens = [int(n) for n in lengths] if lengths is not None else [int(len(w)) for w in waves]
     if any(n > 480000 for n in lens):
         raise ValueError("label_corpus takes clips of at most 30 s; split longer files first (infer.split_audio)")
     etype = model.encoder_type
-    plan = shard.plan_shards(lens, world, etype)
     labeler = Labeler(model, median_filter=median_filter, merge_mode=merge_mode,
                       confidence_threshold=confidence_threshold)
     bucket = 480000 if etype == "whisper" else bucket_samples  # Whisper pads every clip to 30 s itself
+    if shard_by == "batch":
+        batches = shard.plan_batches(lens, world, etype, max_clips, max_samples_per_batch, bucket)[rank]
+    elif shard_by == "utterance":
+        plan = shard.plan_shards(lens, world, etype)
+        batches = shard.bucket_batches(plan[rank], lens, max_clips, max_samples_per_batch, bucket)
+    else:
+        raise ValueError(f"unknown shard_by {shard_by!r}")
     local = []
     pending = None  # (group, T, pinned records, pinned counts, event) of the batch whose results are still in flight
 
@@ -38,44 +85,52 @@ def label_corpus(model, waves, lang_ids=None, *, median_filter=1, merge_mode="ri
         for j, i in enumerate(group):
             local.append((i, raw[j * T:j * T + int(counts[j])].copy()))
 
-    # two pinned staging buffers, sized for the largest batch once (cudaHostAlloc per batch costs more than the batch's
-    # kernels); buffer k % 2 is free again when batch k - 2 has been collected
-    batches = shard.bucket_batches(plan[rank], lens, max_clips, max_samples_per_batch, bucket)
-    cap = max((len(g) * p for p, g in batches), default=0)
-    staging = [torch.empty(cap, dtype=torch.float32).pin_memory() for _ in range(2)] if cap else []
-    for k, (padded, group) in enumerate(batches):
-        host = staging[k & 1][:len(group) * padded].view(len(group), padded)
-        host.zero_()
-        for j, i in enumerate(group):
-            host[j, :lens[i]] = torch.from_numpy(np.asarray(waves[i], dtype=np.float32))
-        wave = host.to(dev, non_blocking=True)
-        lang = None
-        if lang_ids is not None:
-            lang = torch.tensor([lang_ids[i] for i in group], dtype=torch.long).pin_memory().to(dev, non_blocking=True)
-        logits, offsets = model(wave, lang)
-        T = logits.shape[1]
-        # like the reference's batched caller (REF/train.py:485-495): decode each item on its own frame count
-        valid = torch.tensor([min(T, shard.frames_for(lens[i], etype, model.arch.get("hop", 320))) for i in group],
-                             dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
-        _, merged, nout, fcb, n_files = labeler.postprocess(logits, offsets, valid)
-        # results leave through pinned buffers; the host decodes batch k-1 while batch k runs on the GPU
-        rec = torch.empty(merged.shape, dtype=torch.uint8).pin_memory()
-        cnt = torch.empty(n_files, dtype=torch.int32).pin_memory()
-        rec.copy_(merged, non_blocking=True)
-        cnt.copy_(nout[:n_files], non_blocking=True)
-        done = torch.cuda.Event()
-        done.record()
+    # pinned staging buffers sized for the largest batch once (cudaHostAlloc per batch costs more than the batch's
+    # kernels), filled by worker threads one batch ahead; buffer k % depth is free again when batch k - depth + 1 has
+    # been copied (the copy of batch k is stream-ordered before batch k's kernels, collected two batches later)
+    stager = _Stager(batches, lens, waves, workers=stage_workers)
+    hop = model.arch.get("hop", 320)
+    result_pool = {}
+    stager.submit(0)
+    with torch.cuda.device(dev):
+        for k, (padded, group) in enumerate(batches):
+            host = stager.get(k)
+            stager.submit(k + 1)  # filled while this batch's launches are issued and the GPU works
+            wave = host.to(dev, non_blocking=True)
+            lang = None
+            if lang_ids is not None:
+                lang = torch.tensor([lang_ids[i] for i in group], dtype=torch.long).pin_memory().to(dev, non_blocking=True)
+            logits, offsets = model.forward_views(wave, lang)  # consumed by postprocess right away: no clone needed
+            T = logits.shape[1]
+            # like the reference's batched caller (REF/train.py:485-495): decode each item on its own frame count
+            valid = torch.tensor([min(T, shard.frames_for(lens[i], etype, hop)) for i in group],
+                                 dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+            _, merged, nout, fcb, n_files = labeler.postprocess(logits, offsets, valid)
+            # results leave through pinned buffers (two per shape, alternating); the host decodes batch k-1 while
+            # batch k runs on the GPU
+            key = (tuple(merged.shape), n_files, k & 1)
+            if key not in result_pool:
+                result_pool[key] = (torch.empty(merged.shape, dtype=torch.uint8).pin_memory(),
+                                    torch.empty(n_files, dtype=torch.int32).pin_memory())
+            rec, cnt = result_pool[key]
+            rec.copy_(merged, non_blocking=True)
+            cnt.copy_(nout[:n_files], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            if pending is not None:
+                collect(pending)
+            pending = (group, T, rec, cnt, done)
         if pending is not None:
             collect(pending)
-        pending = (group, T, rec, cnt, done)
-    if pending is not None:
-        collect(pending)
+    stager.close()
+    if not gather:
+        return local
     gathered = shard.gather_segments(local, dev)
     if gathered is None:
         return None
     names = labeler.out_names
     out = []
-    for i in range(len(waves)):  # .tolist() converts a whole column at once (69 k segments: 70 ms -> 15 ms)
+    for i in range(len(lens)):  # .tolist() converts a whole column at once (69 k segments: 70 ms -> 15 ms)
         rec = gathered[i]
         out.append(list(zip(rec["start"].tolist(), rec["end"].tolist(), [names[p] for p in rec["ph"].tolist()])))
     return out

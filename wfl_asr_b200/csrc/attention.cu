@@ -484,10 +484,10 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
     if (rc) return rc;
   }
   auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation and device
+  if (configured.needed()) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   dim3 grid((T + 127) / 128, H, B);
   {

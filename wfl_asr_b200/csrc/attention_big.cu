@@ -364,10 +364,10 @@ static int launch_big(const void* qkv, int64_t row_stride, int64_t batch_stride,
     if (rc) return rc;
   }
   auto kern = attention_big_kernel<HD>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation and device
+  if (configured.needed()) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   dim3 grid((T + 127) / 128, H * 2, B);
   {

@@ -32,6 +32,16 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
+// Kernel attributes (max dynamic shared memory, non-portable cluster sizes) and occupancy figures belong to a
+// device's context: a process that labels on several GPUs (infer.py -d cuda:1 after cuda:0) must set / query them
+// once per DEVICE, not once per process.  One bit per device ordinal (0..63).
+int current_device();
+struct PerDeviceOnce {
+  unsigned long long mask = 0;
+  bool needed() const { return ((mask >> current_device()) & 1ull) == 0; }
+  void done() { mask |= 1ull << current_device(); }
+};
+
 // Builds a tiled tensor map (rank 2 or 3, innermost dim first).  strides_bytes has rank-1 entries
 // (stride of dim1, dim2).  Returns 0 or a negative WFL error.
 int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base,

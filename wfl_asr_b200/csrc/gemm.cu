@@ -436,10 +436,10 @@ template <int BN, int OUT_MODE, bool PAIR>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mw, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, PAIR>;
   auto kern = gemm_kernel<BN, OUT_MODE, PAIR>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDeviceOnce configured;  // per instantiation and device
+  if (configured.needed()) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured.done();
   }
   static const bool no_pdl = getenv("WFL_NO_PDL_GEMM") != nullptr;
   static const int no_pdl_mode = getenv("WFL_NO_PDL_GEMM_MODE") ? atoi(getenv("WFL_NO_PDL_GEMM_MODE")) : -1;

@@ -197,10 +197,10 @@ extern "C" int wfl_whisper_logmel(const float* wave, int64_t wave_stride, int32_
   WFL_CHECK_ARG(n_samples >= 1 && wave_stride >= (n_samples < kPadSamples ? n_samples : kPadSamples),
                 "wfl_whisper_logmel: n_samples/wave_stride invalid");
   if (B <= 0) return WFL_OK;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.needed()) {
     WFL_CUDA(cudaFuncSetAttribute(logmel_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
-    configured = true;
+    configured.done();
   }
   WFL_CUDA(cudaMemsetAsync(scratch_max, 0, sizeof(unsigned) * B, stream));
   {
@@ -275,10 +275,10 @@ extern "C" int wfl_mel_power(const float* wave, int64_t wave_stride, int32_t n_s
   WFL_CHECK_ARG(n_samples > kNfft / 2 && wave_stride >= n_samples, "wfl_mel_power: n_samples %d must exceed %d",
                 n_samples, kNfft / 2);
   if (B <= 0) return WFL_OK;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.needed()) {
     WFL_CUDA(cudaFuncSetAttribute(logmel_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostSmem));
-    configured = true;
+    configured.done();
   }
   const int frames = 1 + n_samples / hop;
   const int64_t plane_rows = frames - 1 + (kNfft + hop - 1) / hop;  // rows of the strided view covering n + n_fft samples

@@ -271,10 +271,10 @@ static int launch_lstm_nb(const float* gx, const void* whh, int B, int T, void* 
   constexpr int kLstmCluster = CL;
   constexpr int kLstmNB = NB;
   if (CL > 8) {
-    static bool allowed = false;
-    if (!allowed) {
+    static PerDeviceOnce allowed;
+    if (allowed.needed()) {
       WFL_CUDA(cudaFuncSetAttribute(lstm_kernel<H, CL, NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-      allowed = true;
+      allowed.done();
     }
   }
   cudaLaunchConfig_t cfg = {};
@@ -304,7 +304,9 @@ static int launch_lstm(const float* gx, const void* whh, int B, int T, void* y_f
     const char* e = getenv("WFL_LSTM_NB");
     return e ? atoi(e) : 0;
   }();
-  static const int capacity = [] {
+  static int capacity_of[64] = {0};  // resident clusters per device ordinal (0 = not probed yet)
+  int& capacity = capacity_of[current_device()];
+  if (capacity == 0) capacity = [] {
     using Cfg = LstmCfg<H, CL, 8>;
     if (CL > 8) cudaFuncSetAttribute(lstm_kernel<H, CL, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};

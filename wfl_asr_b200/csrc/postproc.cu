@@ -259,15 +259,14 @@ __global__ void __launch_bounds__(32) merge_kernel(const wfl_segment* __restrict
       const bool head = valid && (mode == WFL_MERGE_NONE || cls != left_cls);
       const unsigned m_valid = __ballot_sync(0xffffffffu, valid);
       const unsigned m_head = __ballot_sync(0xffffffffu, head);
-      if (valid) {
-        const int slot = count + __popc(m_head & (lt_mask | (1u << lane))) - 1;  // slot of the run this segment is in
-        if (head) {
-          dst[slot] = s;
-        }
-        // the last member of a run inside this group supplies the run's end (later groups overwrite in order)
-        const bool next_is_head_or_end = (lane == 31) || !((m_valid >> (lane + 1)) & 1u) || ((m_head >> (lane + 1)) & 1u);
-        if (!head && next_is_head_or_end) dst[slot].end = s.end;
-      }
+      const int slot = count + __popc(m_head & (lt_mask | (1u << lane))) - 1;  // slot of the run this segment is in
+      if (valid && head) dst[slot] = s;
+      // the head's whole-record store (it carries the head's own .end) must be ordered before another lane of this
+      // warp overwrites .end with the run's end: independent thread scheduling gives no order between divergent stores
+      __syncwarp();
+      // the last member of a run inside this group supplies the run's end (later groups overwrite in order)
+      const bool next_is_head_or_end = (lane == 31) || !((m_valid >> (lane + 1)) & 1u) || ((m_head >> (lane + 1)) & 1u);
+      if (valid && !head && next_is_head_or_end) dst[slot].end = s.end;
       __syncwarp();
       count += __popc(m_head);
       const int last = 31 - __clz(m_valid);

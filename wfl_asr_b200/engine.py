@@ -299,6 +299,12 @@ class Engine:
             out.append(n)
         return out
 
+    def live_buffers(self):
+        """References to every cached device buffer a pass just used (workspaces, sub-batch outputs, WavLM rel-bias
+        tables).  A captured CUDA graph holds them so that the one-shape-each caches can evict without freeing memory
+        the graph still addresses."""
+        return (dict(self._ws), dict(self._full_out), dict(getattr(self, "_rel_tables", {})))
+
     # ------------------------------------------------------------------------------------ building blocks
     def _linear(self, a, name, out, M, K, **kw):
         """Flat [M, K] @ W^T over all B*T rows."""

@@ -146,6 +146,8 @@ class _Session:
         if not str(device).startswith("cuda") or not torch.cuda.is_available():
             raise RuntimeError("wfl_asr_b200 runs on a CUDA device only (no CPU path); got device=%r" % (device,))
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         model = BIOPhonemeTagger(self.config, self.labels)
         state_dict = torch.load(checkpoint_path, map_location="cpu", weights_only=True)
         model.load_state_dict(state_dict)
@@ -213,8 +215,7 @@ def _forward_clips(sess, clip_rows, lens, lang_id, batch_clips=32):
                 wave = torch.stack([clip_rows[i][:ln] for i in idx])
             if len(lang_ids) == 1:
                 lt = torch.full((len(idx),), lang_ids[0], dtype=torch.long, device=dev)
-                lg, of = model(wave, lt)
-                acc_l, acc_o = lg.clone(), of.clone()
+                acc_l, acc_o = model(wave, lt)  # fresh tensors (model.forward clones the engine's views)
             else:  # REF/infer.py:265-276: mean over languages when --lang-id is unset (encoder runs once here)
                 acc_l, acc_o = model.forward_language_mean(wave, lang_ids)
             for j, i in enumerate(idx):
@@ -322,9 +323,10 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
                 confidence_threshold=0.0):
     """REF/infer.py:186-328."""
     sess = _Session.get(config_path, checkpoint_path, device)
-    f = _prepare_file(sess, audio_path)
-    segments_pred = _label_files(sess, [f], lang_id, confidence_threshold)[0]
-    return _finish_file(f, segments_pred, output_lab_path)
+    with torch.cuda.device(sess.device):  # every launch below goes to the streams of the session's device (-d cuda:1)
+        f = _prepare_file(sess, audio_path)
+        segments_pred = _label_files(sess, [f], lang_id, confidence_threshold)[0]
+        return _finish_file(f, segments_pred, output_lab_path)
 
 
 def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_path: str = "best_model.pt",
@@ -339,7 +341,7 @@ def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_
     sess = _Session.get(config_path, checkpoint_path, device)
     results = {}
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=max(1, decode_workers)) as pool:
+    with torch.cuda.device(sess.device), ThreadPoolExecutor(max_workers=max(1, decode_workers)) as pool:
         for s0 in range(0, len(wav_files), max(1, files_per_pass)):
             names = wav_files[s0:s0 + max(1, files_per_pass)]
             paths = [str(os.path.join(folder_path, w)) for w in names]

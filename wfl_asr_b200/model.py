@@ -175,6 +175,17 @@ class BIOPhonemeTagger(nn.Module):
         self.conformer_kernel = m.get("conformer_kernel_size", 31)
         d = self.arch["d"]
         self.hidden_size = d
+        # Shapes on which the reference itself fails or changes meaning are rejected here instead of loading and giving
+        # different logits: nn.MultiheadAttention asserts embed_dim % num_heads == 0 (REF/model.py:26); an even
+        # Conformer kernel makes Conv1d(padding=k//2) emit T+1 frames, which the reference trims (REF/model.py:46-49)
+        # -- a different tap alignment than the symmetric padding built here; an even dilated kernel SHORTENS the
+        # sequence in the reference (padding=dil*(k-1)//2, REF/model.py:126-133).
+        if d % self.conformer_heads != 0:
+            raise ValueError(f"embed_dim {d} must be divisible by conformer_heads {self.conformer_heads}")
+        if self.conformer_kernel % 2 == 0:
+            raise ValueError(f"conformer_kernel_size {self.conformer_kernel} must be odd (even sizes are not built)")
+        if self.enable_dilated_conv and self.dilated_conv_kernel % 2 == 0:
+            raise ValueError(f"dilated_conv_kernel {self.dilated_conv_kernel} must be odd (even sizes are not built)")
 
         if self.arch["type"] == "none":
             self.encoder = None
@@ -240,9 +251,21 @@ class BIOPhonemeTagger(nn.Module):
     @torch.no_grad()
     def forward(self, input_values, lang_id=None, max_label_len=None):
         """input_values [B, N] 16 kHz fp32 -> (logits [B, T, L], offsets [B, T, 2])  (REF/model.py:148-194)."""
+        logits, offsets = self.forward_views(input_values, lang_id, max_label_len)
+        # fresh, contiguous tensors like the reference returns: the engine's outputs are views of a workspace that the
+        # next forward of the same shape overwrites (REF/infer.py:268-275 keeps one logits tensor per language in a
+        # list and averages them afterwards -- with aliased views the mean would silently equal the last language)
+        return logits.clone(memory_format=torch.contiguous_format), offsets.clone()
+
+    @torch.no_grad()
+    def forward_views(self, input_values, lang_id=None, max_label_len=None):
+        """Internal zero-copy form of ``forward``: returns VIEWS of the engine's workspace (logits rows are strided),
+        valid until the next forward of the same shape.  pipeline.Labeler consumes them immediately."""
         if self.training:
             raise RuntimeError("wfl_asr_b200.BIOPhonemeTagger is inference-only (eval mode); training is out of scope")
-        return self.engine().forward(input_values, lang_id, max_label_len)
+        eng = self.engine()
+        with torch.cuda.device(eng.dev):
+            return eng.forward(input_values, lang_id, max_label_len)
 
     @torch.no_grad()
     def forward_language_mean(self, input_values, lang_ids):
@@ -253,7 +276,9 @@ class BIOPhonemeTagger(nn.Module):
         lang_ids = [int(i) for i in lang_ids]
         if not lang_ids:
             raise ValueError("lang_ids is empty")
-        outs = self.engine().forward_languages(input_values, lang_ids)
+        eng = self.engine()
+        with torch.cuda.device(eng.dev):
+            outs = eng.forward_languages(input_values, lang_ids)
         # same accumulation order as the reference: torch.stack(...).mean(0) over languages in id order
         logits = torch.stack([o[0] for o in outs]).mean(dim=0)
         offsets = torch.stack([o[1] for o in outs]).mean(dim=0)

@@ -10,9 +10,27 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, MERGE_MODES, OUT_ADD_F32, OUT_G
                    OUT_STORE_F32, GemmDesc, Segment, WflError)
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
-TIMING = None  # bench.py sets this to a list: timed GEMM launches append (tag, algorithmic flops, start, end events)
-TIMING_MIN_SLABS = 1  # only launches with at least this many K-slabs are bracketed by events (event records between
-#                       kernels defeat programmatic dependent launch, so the timed region brackets the dominant kernel only)
+TIMING = None  # bench.py sets this to a list: timed launches append (kind, tag, algorithmic work, start, end events);
+#                work is FLOPs for kind "gemm" / "attention", bytes for the memory-bound kinds, steps for "lstm"
+TIMING_MIN_SLABS = 1  # GEMMs: only launches with at least this many K-slabs are bracketed by events (event records
+#                       between kernels defeat programmatic dependent launch, so the timed region brackets the dominant
+#                       kernel only); the other kinds are bracketed only when TIMING_KINDS names them
+TIMING_KINDS = ()
+
+
+def _t0(kind):
+    if TIMING is None or kind not in TIMING_KINDS:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _t1(e0, kind, tag, work):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        TIMING.append((kind, tag, float(work), e0, e1))
 
 
 def _count(n=1):
@@ -65,7 +83,7 @@ def gemm(a, w, out, *, n, slab_k, shifts=(0,), cols=(0,), a_rows, a_cols, a_row_
     if timed:
         e1.record()
         tag = f"M{batches * d.m_rows}xN{n}xK{len(shifts) * slab_k}/slabs{len(shifts)}/mode{out_mode}" + (f"/g{groups}" if groups > 1 else "")
-        TIMING.append((tag, 2.0 * groups * batches * d.m_rows * n * len(shifts) * slab_k, e0, e1))
+        TIMING.append(("gemm", tag, 2.0 * groups * batches * d.m_rows * n * len(shifts) * slab_k, e0, e1))
     _count()
 
 
@@ -78,18 +96,24 @@ def linear(a2d, w, out2d, **kw):
 
 def attention(qkv, out, *, B, T, H, hd, scale, q_col, k_col, v_col, rel_bias=None, gate=None):
     """qkv f16 [B, T, W]; out f16 [B, T, H*hd]."""
+    e0 = _t0("attention")
     rc = _lib.load().wfl_attention(_ptr(qkv), qkv.stride(1), qkv.stride(0), q_col, k_col, v_col, B, T, H, hd, scale,
                                    _ptr(rel_bias), _ptr(gate), _ptr(out), out.stride(1), out.stride(0), _stream())
     _lib.check(rc, "wfl_attention")
+    _t1(e0, "attention", f"attention hd{hd} H{H} T{T} B{B}" + ("+relbias" if rel_bias is not None else ""), 4.0 * B * H * T * T * hd)
     _count()
 
 
 def layernorm(x, gamma, beta, *, out_f32=None, out_f16=None, gamma2=None, beta2=None, eps=1e-5, act_f16=ACT_NONE,
               rows=None):
     rows = x.numel() // x.shape[-1] if rows is None else rows
+    e0 = _t0("layernorm")
     rc = _lib.load().wfl_layernorm(_ptr(x), rows, x.shape[-1], _ptr(gamma), _ptr(beta), _ptr(gamma2), _ptr(beta2), eps,
                                    _ptr(out_f32), _ptr(out_f16), act_f16, _stream())
     _lib.check(rc, "wfl_layernorm")
+    d = x.shape[-1]  # algorithmic bytes: fp32 row in, f16 and/or fp32 row out
+    _t1(e0, "layernorm", f"layernorm d{d}" + ("+f32out" if out_f32 is not None else "") + ("+2nd" if gamma2 is not None else ""),
+        rows * d * (4 + (2 if out_f16 is not None else 0) + (4 if out_f32 is not None else 0)))
     _count()
 
 
@@ -113,7 +137,9 @@ def wavlm_gate(x_f16, row_stride, B, T, H, hd, gw, gb, gconst, gate):
 
 def split_f16(x, out):
     rows = x.numel() // x.shape[-1]
+    e0 = _t0("split_f16")
     _lib.check(_lib.load().wfl_split_f16(_ptr(x), rows, x.shape[-1], _ptr(out), _stream()), "wfl_split_f16")
+    _t1(e0, "split_f16", f"split_f16 d{x.shape[-1]}", rows * x.shape[-1] * 8)  # fp32 in, [hi | lo] f16 out
     _count()
 
 
@@ -196,33 +222,42 @@ def gather_cols(src, dst, groups, w_in, w_out):
 
 def decode_frames(logits2d, L, o_id, threshold, ids):
     rows = logits2d.shape[0]
+    e0 = _t0("decode_frames")
     rc = _lib.load().wfl_decode_frames(_ptr(logits2d), rows, L, logits2d.stride(0), o_id, threshold, _ptr(ids), _stream())
     _lib.check(rc, "wfl_decode_frames")
+    _t1(e0, "decode_frames", f"decode_frames L{L}", rows * (4 * L + 4))  # 4L + 4 B/frame
     _count()
 
 
 def median_filter(ids_in, ids_out, lengths, k):
     n_clips, stride = ids_in.shape
+    e0 = _t0("median_filter")
     rc = _lib.load().wfl_median_filter(_ptr(ids_in), _ptr(ids_out), _ptr(lengths), n_clips, stride, k, _stream())
     _lib.check(rc, "wfl_median_filter")
+    _t1(e0, "median_filter", f"median_filter k{k}", n_clips * stride * 8)  # int32 in + out
     _count()
 
 
 def bio_decode(ids, offsets, lengths, label_kind, label_ph, frame_duration, time_shift, segs, nseg):
     n_clips, stride = ids.shape
+    e0 = _t0("bio_decode")
     rc = _lib.load().wfl_bio_decode(_ptr(ids), _ptr(offsets), _ptr(lengths), n_clips, stride, _ptr(label_kind),
                                     _ptr(label_ph), label_kind.numel(), frame_duration, _ptr(time_shift), _ptr(segs),
                                     _ptr(nseg), _stream())
     _lib.check(rc, "wfl_bio_decode")
+    # ids (4 B/frame) + the two offsets (8 B/frame) read; 24 B per segment written (count unknown on the host: left out)
+    _t1(e0, "bio_decode", "bio_decode", n_clips * stride * (4 + (8 if offsets is not None else 0)))
     _count()
 
 
 def merge_segments(segs, nseg, clip_stride, file_clip_begin, n_files, ph_class, mode, out, nout):
     if mode not in MERGE_MODES:
         raise ValueError(f"Unsupported merge mode: {mode}")  # REF/utils.py:185
+    e0 = _t0("merge_segments")
     rc = _lib.load().wfl_merge_segments(_ptr(segs), _ptr(nseg), clip_stride, _ptr(file_clip_begin), n_files,
                                         _ptr(ph_class), MERGE_MODES[mode], _ptr(out), _ptr(nout), _stream())
     _lib.check(rc, "wfl_merge_segments")
+    _t1(e0, "merge_segments", f"merge_segments {mode}", 0)  # 2 x 24 B per segment; segment count lives on the device
     _count()
 
 
@@ -233,6 +268,8 @@ def htk_times(segs, n, start_out, end_out):
 
 def lstm_layer(gx, whh, B, T, H, y_f16=None, y_f32=None):
     """gx fp32 [B, T, 8H] (columns [dir][unit][gate]); whh f16 [2, 4H, H] -> y [B, T, 2H]."""
+    e0 = _t0("lstm")
     rc = _lib.load().wfl_lstm_layer(_ptr(gx), _ptr(whh), B, T, H, _ptr(y_f16), _ptr(y_f32), _stream())
     _lib.check(rc, "wfl_lstm_layer")
+    _t1(e0, "lstm", f"lstm H{H} B{B} T{T}", T)  # latency-bound: work = serial steps
     _count()

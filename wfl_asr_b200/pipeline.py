@@ -50,6 +50,10 @@ class _GraphedPass:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = labeler._pass(self.wave, self.lang)
+        # The graph has raw pointers into the engine's and the labeler's workspaces (and the WavLM rel-bias table)
+        # baked in; those caches keep ONE shape each and drop it when another shape comes through.  The graph owns
+        # a reference to everything it captured, so replaying shape A after shape B never touches freed memory.
+        self.keep = (labeler.model.engine().live_buffers(), dict(labeler._ws))
 
     def replay(self, lang_id):
         if self.lang is not None:
@@ -116,6 +120,10 @@ class Labeler:
         """logits [B,T,L] fp32, offsets [B,T,2] fp32 (device) -> (merged segs [B,T] records, nout [n_files]).
         Launches: decode_frames, median_filter (if size > 1), bio_decode, merge_segments."""
         B, T, L = logits.shape
+        with torch.cuda.device(self.dev):
+            return self._postprocess(logits, offsets, lengths, file_clip_begin, time_shift, B, T, L)
+
+    def _postprocess(self, logits, offsets, lengths, file_clip_begin, time_shift, B, T, L):
         ws = self._buffers(B, T)
         if lengths is None:  # full-length clips, one file per clip: constant index vectors, built once per shape
             lengths = ws.get("full_lengths")
@@ -138,9 +146,17 @@ class Labeler:
         return ids, ws["merged"], ws["nout"], file_clip_begin, n_files
 
     def _pass(self, wave, lang_id):
-        logits, offsets = self.model(wave, lang_id)
+        # engine views (no clone): consumed by postprocess before the next pass can overwrite them
+        logits, offsets = self.model.forward_views(wave, lang_id)
         _, merged, nout, fcb, n_files = self.postprocess(logits, offsets)
         return merged, nout, fcb, n_files, logits.shape[1]
+
+    @torch.no_grad()
+    def label_device(self, wave, lang_id=None):
+        """wave [B, N] fp32 on the device -> (merged segment records [B, T] on the device, counts [B], T); nothing is
+        copied to the host.  The records live in the labeler's workspace until the next pass of the same shape."""
+        merged, nout, fcb, n_files, T = self._pass(wave, lang_id)
+        return merged, nout, T
 
     def _run(self, wave, lang_id):
         """One pass over a device buffer that will be reused by later calls: replayed from a CUDA graph when enabled."""
@@ -158,7 +174,7 @@ class Labeler:
     @torch.no_grad()
     def label(self, wave, lang_id=None, file_clip_begin=None, time_shift=None):
         """wave [B, N] fp32 on the device -> list (per file) of [(start, end, phoneme)] python tuples."""
-        logits, offsets = self.model(wave, lang_id)
+        logits, offsets = self.model.forward_views(wave, lang_id)
         _, merged, nout, fcb, n_files = self.postprocess(logits, offsets, None, file_clip_begin, time_shift)
         return self.fetch(merged, nout, fcb, n_files, logits.shape[1])
 
@@ -184,6 +200,9 @@ class Labeler:
         dev = self.dev
         main = torch.cuda.current_stream(dev)
         copy = torch.cuda.Stream(dev)
+        # the staging slots persist across calls: a previous call (or an abandoned generator) may still have kernels
+        # in flight on the main stream that read them, so this call's first copies queue behind the main stream
+        copy.wait_stream(main)
         it = iter(host_batches)
         slots = self._stream_slots  # device staging (double buffered); persistent so captured graphs stay valid
         ready = [torch.cuda.Event(), torch.cuda.Event()]

@@ -65,6 +65,30 @@ def bucket_batches(indices, n_samples_per_utt, max_clips, max_samples_per_batch,
     return batches
 
 
+def plan_batches(n_samples_per_utt, world_size, encoder_type="whisper", max_clips=32, max_samples_per_batch=32 * 480000,
+                 bucket_samples=8000):
+    """Shards BATCHES instead of utterances: the corpus is length-bucketed into batches first (independent of the
+    world size), then whole batches are dealt to ranks longest-processing-time first on the summed utterance cost.
+    Dealing single utterances (``plan_shards``) spreads every length bucket over all ranks, so at 8 ranks each rank
+    is left with 1/8 of every bucket and runs small, badly filled batches; dealing batches keeps them full on every
+    rank, and -- because a clip's padded length and the kernels' arithmetic do not depend on its batch mates -- the
+    results are the same for every world size.  Returns a list (per rank) of (padded_length, [utterance indices])."""
+    batches = bucket_batches(range(len(n_samples_per_utt)), n_samples_per_utt, max_clips, max_samples_per_batch,
+                             bucket_samples)
+    hop = 320
+    costs = [sum(cost(frames_for(padded, encoder_type, hop)) for _ in group) for padded, group in batches]
+    order = sorted(range(len(batches)), key=lambda k: (-costs[k], k))
+    heap = [(0.0, r) for r in range(world_size)]
+    heapq.heapify(heap)
+    per_rank = [[] for _ in range(world_size)]
+    for k in order:
+        load, r = heapq.heappop(heap)
+        per_rank[r].append(k)
+        heapq.heappush(heap, (load + costs[k], r))
+    # inside a rank: longest first, so the largest workspaces are sized once and the tail is short batches
+    return [[batches[k] for k in sorted(ks, key=lambda k: (-batches[k][0], k))] for ks in per_rank]
+
+
 def gather_segments(local, device):
     """``local``: list of (utterance index, numpy structured array of SEG_DTYPE records) on this rank.
     Returns on rank 0 a dict {utterance index: records}; None elsewhere.  Payload is KBs: latency, not bandwidth."""

@@ -86,3 +86,36 @@ def bench_model(cls, cfg, labels, seed=0, classifier_gain=60.0):
         model.classifier.weight.mul_(classifier_gain)
         model.classifier.bias.mul_(classifier_gain)
     return model
+
+
+class RaggedCorpus:
+    """BASELINE configs[3] corpus: ``n`` utterances with lengths U[2, 30] s drawn with
+    ``numpy.random.default_rng(4242)``.  Utterance i is a window of one of ``pool`` 30 s base clips (synth_wave) scaled
+    by a per-utterance gain; it is materialised when indexed, so a rank only ever builds its own shard
+    (bulk.label_corpus indexes nothing else when ``lengths`` is passed)."""
+
+    def __init__(self, n, seed=4242, pool=8, sr=16000, min_s=2.0, max_s=30.0):
+        rng = np.random.default_rng(seed)
+        self.seconds = rng.uniform(min_s, max_s, size=n)
+        self.lengths = [int(s * sr) for s in self.seconds]
+        self.starts = [int(rng.integers(0, int(max_s * sr) - ln + 1)) for ln in self.lengths]
+        self.gains = 0.5 + 0.5 * rng.random(n)
+        self.sr = sr
+        self._pool_size = pool
+        self._pool = None
+
+    def _base(self, k):
+        if self._pool is None:
+            self._pool = [synth_wave(7000 + j, 30.0, self.sr).astype(np.float32) for j in range(self._pool_size)]
+        return self._pool[k]
+
+    def __len__(self):
+        return len(self.lengths)
+
+    def __getitem__(self, i):
+        s, n = self.starts[i], self.lengths[i]
+        return self._base(i % self._pool_size)[s:s + n] * np.float32(self.gains[i])
+
+    @property
+    def audio_seconds(self):
+        return float(sum(self.lengths)) / self.sr

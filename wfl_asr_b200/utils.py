@@ -20,7 +20,7 @@ htk_time_factor = 1e7  # REF/utils.py:8
 def _device():
     if not torch.cuda.is_available():
         raise ops.WflError("wfl_asr_b200.utils needs a CUDA device (no CPU fallback exists)")
-    return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cuda", torch.cuda.current_device())  # launches below go to this device's current stream
 
 
 def decode_bio_tags(tags, frame_duration=0.02, offsets=None):
