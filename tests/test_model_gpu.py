@@ -67,9 +67,12 @@ def test_forward_matches_oracle(name):
     # leaves room for one or two near-tie frames at these small test sizes)
     assert rel <= 2e-3, f"logit error {rel} above the fp16 bar 2e-3 (north_star tolerance 1e-2)"
     assert agree_safe == 1.0
-    # north_star bar 99.9 %; a fixture with fewer than 1000 frames may lose at most one near-tie frame
+    # north_star bar 99.9 %, asserted as such on the full-size clips (test_full_size_*); these fixtures are one or two
+    # short clips of random-init logits (about 1 % of their frames have a top-2 margin below twice the logit error), so
+    # the raw bar here leaves room for two near-tie frames -- every frame outside that margin must agree (above)
     frames = ref_l.shape[0] * ref_l.shape[1]
-    assert agree >= min(NORTH_STAR_TAG_AGREEMENT, 1.0 - 1.0 / frames) - 1e-9
+    mismatched = int((logits.argmax(-1) != ref_l.argmax(-1)).sum())
+    assert mismatched <= max(2, int(frames * (1.0 - NORTH_STAR_TAG_AGREEMENT))), f"{mismatched} of {frames} frames differ"
     assert off_err <= 2e-3
 
 
@@ -474,8 +477,9 @@ def test_full_size_cfg2_properties():
     for i in (0, 13, 31):
         li, oi = model(wave[i:i + 1].to(DEV), lang[i:i + 1])
         assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch 32 and batch 1"
-    ref_l, ref_o = to.forward(wave[13:14], sd, cfg, lang[13:14].cpu())
-    rel, agree, agree_safe, off_err = _compare("cfg2 full size, clip 13", l1[13:14].float().cpu(), o1[13:14].float().cpu(), ref_l, ref_o)
+    chk = [1, 4, 7, 10, 13, 16, 19, 22]  # eight full 30 s clips: 12 000 frames against the fp32 oracle
+    ref_l, ref_o = to.forward(wave[chk], sd, cfg, lang[chk].cpu())
+    rel, agree, agree_safe, off_err = _compare(f"cfg2 full size, clips {chk}", l1[chk].float().cpu(), o1[chk].float().cpu(), ref_l, ref_o)
     assert rel <= 2e-3 and agree_safe == 1.0 and agree >= NORTH_STAR_TAG_AGREEMENT
     lab = Labeler(model, median_filter=5, merge_mode="right", confidence_threshold=0.5)
     ids, merged, nout, fcb, n_files = lab.postprocess(l1, o1)
@@ -509,42 +513,45 @@ def test_full_size_cfg3_properties():
     for i in (0, 41, 63):
         li, oi = model(wave[i:i + 1].to(DEV), lang[i:i + 1])
         assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch 64 and batch 1"
-    ref_l, ref_o = to.forward(wave[41:42], sd, cfg, lang[41:42].cpu())
-    rel, agree, agree_safe, off_err = _compare("cfg3 full size, clip 41", l1[41:42].float().cpu(), o1[41:42].float().cpu(), ref_l, ref_o)
+    chk = [0, 21, 41, 62]  # 6 000 frames against the fp32 oracle
+    ref_l, ref_o = to.forward(wave[chk], sd, cfg, lang[chk].cpu())
+    rel, agree, agree_safe, off_err = _compare(f"cfg3 full size, clips {chk}", l1[chk].float().cpu(), o1[chk].float().cpu(), ref_l, ref_o)
     assert rel <= 2e-3 and agree_safe == 1.0 and agree >= NORTH_STAR_TAG_AGREEMENT
 
 
-def _full_size(workload, B, seconds, probe, check_clip, seed0):
+def _full_size(workload, B, seconds, probe, check, seed0):
     """Full-depth model of a BASELINE config on B clips: run-to-run determinism, batch invariance of the probed clips
-    (bitwise), and the fp32 oracle on one clip at the north_star bars (1e-2 logits -- held to 2e-3 --, >= 99.9 % tags)."""
+    (bitwise), and the fp32 oracle on the ``check`` clips at the north_star bars: logits within 1e-2 (held to 2e-3),
+    frame-tag agreement >= 99.9 % over all checked frames."""
     from wfl_asr_b200 import synth
     cfg = synth.workload_config(workload)
     labels = synth.synth_labels(30)
     model = synth.bench_model(BIOPhonemeTagger, cfg, labels)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model = model.to(DEV).eval()
-    base = [synth.synth_wave(seed0 + i, seconds) for i in range(min(B, 4))]
+    base = [synth.synth_wave(seed0 + i, seconds) for i in range(min(B, 8))]
     wave = torch.from_numpy(np.stack([base[i % len(base)] * (0.5 + 0.5 * ((i * 7) % 11) / 11.0) for i in range(B)]).astype(np.float32))
     lang = torch.tensor([i % 2 for i in range(B)], device=DEV)
-    l1, o1 = (t.clone() for t in model(wave.to(DEV), lang))
+    l1, o1 = model(wave.to(DEV), lang)
     l2, o2 = model(wave.to(DEV), lang)
     assert torch.equal(l1, l2) and torch.equal(o1, o2), "forward is not deterministic"
     for i in probe:
         li, oi = model(wave[i:i + 1].to(DEV), lang[i:i + 1])
         assert torch.equal(li[0], l1[i]) and torch.equal(oi[0], o1[i]), f"clip {i} differs between batch {B} and batch 1"
-    c = check_clip
-    ref_l, ref_o = to.forward(wave[c:c + 1], sd, cfg, lang[c:c + 1].cpu())
-    rel, agree, agree_safe, off_err = _compare(f"{workload} full size, clip {c}", l1[c:c + 1].float().cpu(),
-                                               o1[c:c + 1].float().cpu(), ref_l, ref_o)
+    check = list(check)
+    ref_l, ref_o = to.forward(wave[check], sd, cfg, lang[check].cpu())
+    rel, agree, agree_safe, off_err = _compare(f"{workload} full size, clips {check}", l1[check].float().cpu(),
+                                               o1[check].float().cpu(), ref_l, ref_o)
     assert rel <= 2e-3 and agree_safe == 1.0 and off_err <= 2e-3
-    assert agree >= NORTH_STAR_TAG_AGREEMENT
+    assert agree >= NORTH_STAR_TAG_AGREEMENT, f"{workload}: tag agreement {agree:.4%} over {ref_l.shape[0] * ref_l.shape[1]} frames"
     return model, labels, l1, o1
 
 
 def test_full_size_cfg1_properties():
     """BASELINE configs[0] at full size: WavLM-base-plus (12 layers, GroupNorm front-end, post-LN) + 2 Conformer blocks
-    (heads 2 -> head dim 384), batch 1 x 10 s -> 499 frames; plus a batch of 3 to check batch invariance."""
-    model, labels, l1, o1 = _full_size("cfg1", 3, 10.0, probe=(0, 2), check_clip=2, seed0=500)
+    (heads 2 -> head dim 384), 10 s clips -> 499 frames; a batch of 8 (3 992 frames against the oracle) that also
+    checks batch invariance against the batch-1 pass the config names."""
+    model, labels, l1, o1 = _full_size("cfg1", 8, 10.0, probe=(0, 7), check=range(8), seed0=500)
     assert l1.shape[1] == 499
     lab = Labeler(model, median_filter=5, merge_mode="right", confidence_threshold=0.5)
     ids, merged, nout, fcb, n_files = lab.postprocess(l1, o1)
@@ -558,15 +565,15 @@ def test_full_size_cfg1_properties():
 def test_full_size_cfg4_properties():
     """BASELINE configs[3] at full size: WavLM-large (24 pre-LN layers, LayerNorm front-end, input normalisation) + 6
     Conformer blocks with heads 2 -> head dim 512 (attention_big_kernel<512>), d = 1024; 6 clips x 16 s (the corpus'
-    mean utterance length) -> 799 frames."""
-    model, labels, l1, o1 = _full_size("cfg4", 6, 16.0, probe=(0, 5), check_clip=3, seed0=520)
+    mean utterance length) -> 799 frames, 4 of them against the oracle."""
+    model, labels, l1, o1 = _full_size("cfg4", 6, 16.0, probe=(0, 5), check=(0, 2, 3, 5), seed0=520)
     assert l1.shape[1] == 799 and model.engine().conf_hdp == 512
 
 
 def test_full_size_cfg5_properties():
     """BASELINE configs[4] at full size: Whisper-large-v3 (32 layers, d 1280, 20 heads, 128 mels) + BiLSTM(2) with H 640
     (lstm_kernel<640,16,8>) + 8 Conformer blocks with head dim 640 (attention_big_kernel<640>) + dilated stack."""
-    model, labels, l1, o1 = _full_size("cfg5", 4, 30.0, probe=(1,), check_clip=1, seed0=540)
+    model, labels, l1, o1 = _full_size("cfg5", 4, 30.0, probe=(1,), check=(1, 2), seed0=540)
     assert l1.shape[1] == 1500 and model.engine().conf_hdp == 640 and model.engine().lstm_hp == 640
 
 

@@ -48,6 +48,13 @@ class Engine:
         self.L = n_labels
         self.Lp = (n_labels + 7) // 8 * 8
         self.W = {}
+        # Precision tier (tools/precision_attribution.py).  With f16 operands everywhere the logit
+        # error is dominated by the static rounding of a few WEIGHT matrices: the attention value / output projections
+        # (their input -- the context -- is nearly the same vector for every frame of a clip, so the rounding error of
+        # W acts as a per-clip bias that no later normalisation removes) and the first feed-forward after the stream
+        # has been re-created (lang_proj / BiLSTM output).  Those weights are kept as [hi | lo] (two K slabs against the
+        # same f16 activations): +4 d^2 FLOPs per frame and attention layer.  WFL_PRECISION=fast turns it off (A/B runs).
+        self.split_attn = os.environ.get("WFL_PRECISION", "high") != "fast"
         self._ws = {}
         self._full_out = {}
         self._pack(sd)
@@ -61,6 +68,30 @@ class Engine:
         self._put(name + ".w", packing.pad_k(w.float(), _pad64(w.shape[1])), "f16")
         if b is not None:
             self._put(name + ".b", b)
+
+    def _pack_split_attn(self, q, w_v, w_out):
+        """[hi | lo] copies of an attention layer's value and output projection weights (precision tier)."""
+        if self.split_attn:
+            self.W[q + "v.w2"] = packing.split_hi_lo(packing.pad_k(w_v, _pad64(w_v.shape[1])).to(self.dev), parts="hl")
+            self.W[q + "out.w2"] = packing.split_hi_lo(w_out.to(self.dev), parts="hl")
+
+    def _qkv_out(self, h, q, qkv, ctx, x, M, d, attend):
+        """qkv = h W_qkv^T (+ bias); ctx = attend(); x += ctx W_out^T (+ bias) -- with the value / output projection
+        weights in [hi | lo] form when the precision tier is on (q, k rows stay plain)."""
+        w, b = self.W[q + "qkv.w"], self.W[q + "qkv.b"]
+        if self.split_attn:
+            ops.gemm(h, w[:2 * d], qkv, n=2 * d, slab_k=d, a_rows=M, a_cols=d, a_row_stride=h.stride(-2), m_rows=M,
+                     out_row_stride=3 * d, bias=b[:2 * d])
+            ops.gemm(h, self.W[q + "v.w2"], qkv[:, 2 * d:], n=d, slab_k=d, shifts=[0, 0], cols=[0, 0], a_rows=M, a_cols=d,
+                     a_row_stride=h.stride(-2), m_rows=M, out_row_stride=3 * d, bias=b[2 * d:])
+        else:
+            self._linear(h, q + "qkv", qkv, M, d)
+        attend()
+        if self.split_attn:
+            ops.gemm(ctx, self.W[q + "out.w2"], x, n=d, slab_k=d, shifts=[0, 0], cols=[0, 0], a_rows=M, a_cols=d,
+                     a_row_stride=d, m_rows=M, out_row_stride=d, bias=self.W[q + "out.b"], out_mode=ops.OUT_ADD_F32)
+        else:
+            self._linear(ctx, q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
 
     def _pack_ln(self, name, sd, key):
         self._put(name + ".g", sd[key + ".weight"])
@@ -77,12 +108,14 @@ class Engine:
             self._put("mel.fb", sd["mel_extractor.mel_scale.fb"])
         # lang conditioning (REF/model.py:176-180): W [d, d+E] -> W_h and a per-language bias
         w = sd["lang_proj.weight"].float()
-        self._pack_linear("lang", w[:, :d], None)
-        # encoder_type "none": the hidden states are raw mel POWERS (1e-2 .. 1e4 and beyond), so their first projection
-        # (lang_proj, or the BiLSTM input GEMM when no language is given) runs in split precision like the classifier
-        self.raw_hidden = self.arch["type"] == "none"
-        if self.raw_hidden:
-            self.W["lang.w3"] = packing.split_hi_lo(w[:, :d].to(self.dev), dk)
+        # Every contraction whose output BECOMES the hidden state (instead of being added to it as a residual) runs in
+        # split precision like the classifier -- A = [hi | lo], W = [hi | hi | lo], i.e. x_hi w_hi + x_lo w_hi + x_hi w_lo
+        # with ~22 significant bits per operand: lang_proj, the BiLSTM input projections and the dilated stack.  A
+        # residual branch's rounding error enters the stream scaled by the branch's share of it; these enter at full
+        # weight, and on the whisper-base configs they carried 40-45 % of the whole logit error variance (measured with
+        # tools/precision_attribution.py) for 1-3 % of the FLOPs.
+        self.raw_hidden = self.arch["type"] == "none"  # hidden states are raw mel powers: _mel_features leaves the split
+        self.W["lang.w3"] = packing.split_hi_lo(w[:, :d].to(self.dev), dk)
         self._put("lang.bias", sd["lang_emb.weight"].float() @ w[:, d:].T + sd["lang_proj.bias"].float())
         if m.get("enable_bilstm", True):
             self._pack_bilstm(sd)
@@ -101,11 +134,24 @@ class Engine:
                 self._pack_ln(q + ff + ".ln", sd, p + ff + ".net.0")
                 self._pack_linear(q + ff + ".l1", sd[p + ff + ".net.1.weight"], sd[p + ff + ".net.1.bias"])
                 self._pack_linear(q + ff + ".l2", sd[p + ff + ".net.4.weight"], sd[p + ff + ".net.4.bias"])
+                if i == 0 and ff == "ff1" and self.split_attn:  # first residual branch after the stream was re-created
+                    for l in ("l1", "l2"):
+                        wl = sd[p + ff + (".net.1" if l == "l1" else ".net.4") + ".weight"].float()
+                        self.W[q + ff + f".{l}.w2"] = packing.split_hi_lo(packing.pad_k(wl, _pad64(wl.shape[1])).to(self.dev),
+                                                                          parts="hl")
             # q/k/v rows and out_proj columns: 3H (resp. H) head blocks, each padded to the built head dim
-            self._pack_linear(q + "attn.in", packing.pad_blocks(sd[p + "self_attn.in_proj_weight"].float(), 3 * H, hd, hdp, 0),
-                              packing.pad_blocks(sd[p + "self_attn.in_proj_bias"].float(), 3 * H, hd, hdp, 0))
-            self._pack_linear(q + "attn.out", packing.pad_blocks(sd[p + "self_attn.out_proj.weight"].float(), H, hd, hdp, 1),
-                              sd[p + "self_attn.out_proj.bias"])
+            w_in = packing.pad_blocks(sd[p + "self_attn.in_proj_weight"].float(), 3 * H, hd, hdp, 0)
+            w_out = packing.pad_blocks(sd[p + "self_attn.out_proj.weight"].float(), H, hd, hdp, 1)
+            self._pack_linear(q + "attn.in", w_in, packing.pad_blocks(sd[p + "self_attn.in_proj_bias"].float(), 3 * H, hd, hdp, 0))
+            self._pack_linear(q + "attn.out", w_out, sd[p + "self_attn.out_proj.bias"])
+            if self.split_attn:
+                # MHA sits on the un-normalised stream and is followed by ln1(x + attn): the value and output
+                # projections' WEIGHT rounding is the second largest error source after the stream-replacing
+                # contractions (tools/precision_attribution.py: 13 % of the variance on whisper-base + 4 Conformer);
+                # their weights are kept as [hi | lo] (two K slabs against the same f16 activations)
+                aw = H * hdp
+                self.W[q + "attn.v.w2"] = packing.split_hi_lo(packing.pad_k(w_in[2 * aw:], dk).to(self.dev), parts="hl")
+                self.W[q + "attn.out.w2"] = packing.split_hi_lo(w_out.to(self.dev), parts="hl")
             self._pack_ln(q + "ln1", sd, p + "ln1")
             self._pack_ln(q + "ln2", sd, p + "ln2")
             # GLU: value rows and gate rows each padded to dk (padded outputs are 0 * sigmoid(0) = 0)
@@ -120,8 +166,8 @@ class Engine:
         self.dil_depth = m.get("dilated_conv_depth", 2) if m.get("enable_dilated_conv", True) else 0
         self.dil_k = m.get("dilated_conv_kernel", 3)
         for i in range(self.dil_depth):
-            self._pack_linear(f"dil{i}", packing.conv_taps(sd[f"dilated_conv_stack.{2 * i}.weight"].float(), dk),
-                              sd[f"dilated_conv_stack.{2 * i}.bias"])
+            self.W[f"dil{i}.w3"] = packing.split_hi_lo_taps(sd[f"dilated_conv_stack.{2 * i}.weight"].float().to(self.dev), dk)
+            self._put(f"dil{i}.b", sd[f"dilated_conv_stack.{2 * i}.bias"])
         # classifier in split precision: A = [hi | lo], W = [hi | hi | lo]  (x_hi w_hi + x_lo w_hi + x_hi w_lo)
         wc = packing.pad_rows(sd["classifier.weight"].float(), self.Lp)
         self.W["cls.w"] = packing.split_hi_lo(wc.to(self.dev), dk)  # f16 [Lp, 3 dk]
@@ -147,6 +193,7 @@ class Engine:
             bq, bv = sd[p + "self_attn.q_proj.bias"].float(), sd[p + "self_attn.v_proj.bias"].float()
             self._pack_linear(q + "qkv", torch.cat([wq, wk, wv], 0), torch.cat([bq, torch.zeros_like(bq), bv], 0))
             self._pack_linear(q + "out", sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+            self._pack_split_attn(q, wv, sd[p + "self_attn.out_proj.weight"].float())
             self._pack_ln(q + "ln1", sd, p + "self_attn_layer_norm")
             self._pack_ln(q + "ln2", sd, p + "final_layer_norm")
             self._pack_linear(q + "fc1", sd[p + "fc1.weight"], sd[p + "fc1.bias"])
@@ -187,6 +234,7 @@ class Engine:
             self._pack_linear(q + "qkv", torch.cat([sd[p + f"{n}_proj.weight"].float() for n in "qkv"], 0),
                               torch.cat([sd[p + f"{n}_proj.bias"].float() for n in "qkv"], 0))
             self._pack_linear(q + "out", sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+            self._pack_split_attn(q, sd[p + "v_proj.weight"].float(), sd[p + "out_proj.weight"].float())
             self._put(q + "gate.w", sd[p + "gru_rel_pos_linear.weight"])
             self._put(q + "gate.b", sd[p + "gru_rel_pos_linear.bias"])
             self._put(q + "gate.c", sd[p + "gru_rel_pos_const"].float().reshape(-1))
@@ -239,9 +287,11 @@ class Engine:
                 b_in.append(packing.pad_rows(b.view(4, Hs).t().reshape(-1, 1), 4 * Hp).reshape(-1))
                 w = packing.pad_blocks(sd[f"bilstm.weight_hh_l{layer}{suffix}"].float(), 4, Hs, Hp, 0)
                 w_hh.append(packing.pad_k(w, Hp))
-            self._pack_linear(f"lstm{layer}.in", torch.cat(w_in, 0), torch.cat(b_in, 0))
-            if layer == 0 and self.raw_hidden:
+            self._put(f"lstm{layer}.in.b", torch.cat(b_in, 0))
+            if layer == 0:  # input = the fp32 hidden state, split [hi | lo]
                 self.W["lstm0.in.w3"] = packing.split_hi_lo(torch.cat(w_in, 0).to(self.dev), self.dk)
+            else:  # input = the f16 output of the layer below: only the weights are split, [hi | lo]
+                self.W[f"lstm{layer}.in.w2"] = packing.split_hi_lo(torch.cat(w_in, 0).to(self.dev), parts="hl")
             self._put(f"lstm{layer}.whh", torch.stack(w_hh, 0), "f16")
 
     # ------------------------------------------------------------------------------------ workspaces
@@ -352,10 +402,9 @@ class Engine:
         for i in range(a["layers"]):
             q = f"enc{i}."
             self._ln(x, q + "ln1", out_f16=ws["h"])
-            self._linear(ws["h"], q + "qkv", qkv, M, d)
-            ops.attention(qkv.view(B, T, 3 * d), ctx.view(B, T, d), B=B, T=T, H=H, hd=hd,
-                          scale=hd ** -0.5, q_col=0, k_col=d, v_col=2 * d)
-            self._linear(ctx, q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
+            self._qkv_out(ws["h"], q, qkv, ctx, x, M, d, lambda: ops.attention(
+                qkv.view(B, T, 3 * d), ctx.view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5, q_col=0, k_col=d,
+                v_col=2 * d))
             self._ln(x, q + "ln2", out_f16=ws["h"])
             self._linear(ws["h"], q + "fc1", ws["u"], M, d, act=ops.ACT_GELU)
             self._linear(ws["u"], q + "fc2", x, M, a["ffn"], out_mode=ops.OUT_ADD_F32)
@@ -423,12 +472,12 @@ class Engine:
             q = f"wl{i}."
             if large:
                 self._ln(x, q + "ln1", out_f16=ws["h"])
-            self._linear(ws["h"], q + "qkv", qkv, M, d)
-            ops.wavlm_gate(ws["h"], d, B, T, H, hd, self.W[q + "gate.w"], self.W[q + "gate.b"], self.W[q + "gate.c"],
-                           ws["gate"])
-            ops.attention(qkv.view(B, T, 3 * d), ctx.view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5,
-                          q_col=0, k_col=d, v_col=2 * d, rel_bias=tab, gate=ws["gate"])
-            self._linear(ctx, q + "out", x, M, d, out_mode=ops.OUT_ADD_F32)
+            def attend(q=q):
+                ops.wavlm_gate(ws["h"], d, B, T, H, hd, self.W[q + "gate.w"], self.W[q + "gate.b"], self.W[q + "gate.c"],
+                               ws["gate"])
+                ops.attention(qkv.view(B, T, 3 * d), ctx.view(B, T, d), B=B, T=T, H=H, hd=hd, scale=hd ** -0.5,
+                              q_col=0, k_col=d, v_col=2 * d, rel_bias=tab, gate=ws["gate"])
+            self._qkv_out(ws["h"], q, qkv, ctx, x, M, d, attend)
             if large:
                 self._ln(x, q + "ln2", out_f16=ws["h"])
             else:
@@ -462,20 +511,40 @@ class Engine:
         Fd = self.ffx * d
         # x += 0.5 * FF1(x)
         self._ln(x, q + "ff1.ln", out_f16=ws["h"])
-        self._linear(ws["h"], q + "ff1.l1", ws["u"], M, d, act=ops.ACT_GELU)
-        self._linear(ws["u"], q + "ff1.l2", x, M, Fd, out_mode=ops.OUT_ADD_F32, alpha=0.5)
+        if (q + "ff1.l1.w2") in self.W:
+            u = ws["u"]
+            ops.gemm(ws["h"], self.W[q + "ff1.l1.w2"], u, n=Fd, slab_k=self.dk, shifts=[0, 0], cols=[0, 0], a_rows=M,
+                     a_cols=d, a_row_stride=d, m_rows=M, out_row_stride=u.stride(0), bias=self.W[q + "ff1.l1.b"],
+                     act=ops.ACT_GELU)
+            ops.gemm(u, self.W[q + "ff1.l2.w2"], x, n=d, slab_k=_pad64(Fd), shifts=[0, 0], cols=[0, 0], a_rows=M, a_cols=Fd,
+                     a_row_stride=u.stride(0), m_rows=M, out_row_stride=d, bias=self.W[q + "ff1.l2.b"],
+                     out_mode=ops.OUT_ADD_F32, alpha=0.5)
+        else:
+            self._linear(ws["h"], q + "ff1.l1", ws["u"], M, d, act=ops.ACT_GELU)
+            self._linear(ws["u"], q + "ff1.l2", x, M, Fd, out_mode=ops.OUT_ADD_F32, alpha=0.5)
         # x = ln1(x + MHA(x, x, x)); h = ln2(x)
         ops.split_f16(x, ws["hl"])
         hi = ws["hl"]
         w = self.W[q + "attn.in.w"]
         aw = self.conf_aw
         qkv, ctx = _v(ws["qkv"], M, 3 * aw), _v(ws["ctx"], M, aw)
-        ops.gemm(hi, w, qkv, n=3 * aw, slab_k=self.dk, a_rows=M, a_cols=d, a_row_stride=2 * d, m_rows=M,
-                 out_row_stride=3 * aw, bias=self.W[q + "attn.in.b"])
+        b_in = self.W[q + "attn.in.b"]
+        if self.split_attn:  # q, k: plain; v: weights [hi | lo]
+            ops.gemm(hi, w[:2 * aw], qkv, n=2 * aw, slab_k=self.dk, a_rows=M, a_cols=d, a_row_stride=2 * d, m_rows=M,
+                     out_row_stride=3 * aw, bias=b_in[:2 * aw])
+            ops.gemm(hi, self.W[q + "attn.v.w2"], qkv[:, 2 * aw:], n=aw, slab_k=self.dk, shifts=[0, 0], cols=[0, 0],
+                     a_rows=M, a_cols=d, a_row_stride=2 * d, m_rows=M, out_row_stride=3 * aw, bias=b_in[2 * aw:])
+        else:
+            ops.gemm(hi, w, qkv, n=3 * aw, slab_k=self.dk, a_rows=M, a_cols=d, a_row_stride=2 * d, m_rows=M,
+                     out_row_stride=3 * aw, bias=b_in)
         H = self.conf_heads
         ops.attention(qkv.view(B, T, 3 * aw), ctx.view(B, T, aw), B=B, T=T, H=H, hd=self.conf_hdp, scale=(d // H) ** -0.5,
                       q_col=0, k_col=aw, v_col=2 * aw)
-        self._linear(ctx, q + "attn.out", x, M, aw, out_mode=ops.OUT_ADD_F32)
+        if self.split_attn:
+            ops.gemm(ctx, self.W[q + "attn.out.w2"], x, n=d, slab_k=aw, shifts=[0, 0], cols=[0, 0], a_rows=M, a_cols=aw,
+                     a_row_stride=aw, m_rows=M, out_row_stride=d, bias=self.W[q + "attn.out.b"], out_mode=ops.OUT_ADD_F32)
+        else:
+            self._linear(ctx, q + "attn.out", x, M, aw, out_mode=ops.OUT_ADD_F32)
         ops.layernorm(x, self.W[q + "ln1.g"], self.W[q + "ln1.b"], out_f32=x, out_f16=ws["h"],
                       gamma2=self.W[q + "ln2.g"], beta2=self.W[q + "ln2.b"])
         # conv module: pw1 -> GLU -> conv-k (BatchNorm folded) -> GELU -> pw2;  x += conv
@@ -530,13 +599,11 @@ class Engine:
         d = self.d
         enc = ws.get("enc")
         if enc is None:
-            enc = ws["enc"] = torch.empty(B * T, 2 * d if self.raw_hidden else d, device=self.dev, dtype=torch.float16)
+            enc = ws["enc"] = torch.empty(B * T, 2 * d, device=self.dev, dtype=torch.float16)
+        # the [hi | lo] split of the final hidden state, exactly what _head builds for a single-language pass
         if final_ln is not None:
-            self._ln(ws["x"], final_ln, out_f16=enc)
-        elif self.raw_hidden:
-            enc.copy_(ws["hl"])  # the [hi | lo] split of x that _encode left
-        else:
-            enc.copy_(ws["h"])  # wavlm-base(-plus): the last post-LN already left f16(x) in ws["h"]
+            self._ln(ws["x"], final_ln, out_f32=ws["x"])
+        ops.split_f16(ws["x"], enc)
         outs = []
         for lid in lang_ids:
             lt = torch.full((B,), int(lid), dtype=torch.long, device=self.dev)
@@ -567,82 +634,66 @@ class Engine:
         return ws, B, T, final_ln
 
     def _head(self, ws, B, T, final_ln, lang_id, max_label_len, enc=None, dest=None):
-        """Everything after the encoder (REF/model.py:166-194).  ``enc``: f16 encoder output kept by
-        forward_languages (final LayerNorm already applied); otherwise it is produced here from ws["x"] / ws["h"]."""
+        """Everything after the encoder (REF/model.py:166-194).  ``enc``: [hi | lo] f16 split of the final hidden state
+        kept by forward_languages (final LayerNorm already applied); otherwise it is produced here from ws["x"]."""
         d = self.d
         x = ws["x"]
         M = B * T
         bilstm = self.m.get("enable_bilstm", True)
-        # f16 copy of a final_ln-free encoder output: ws["h"] (wavlm-base post-LN) or the hi half of ws["hl"] ("none")
-        raw = self.raw_hidden
-        f16_x, f16_stride = (ws["hl"], 2 * d) if raw else (ws["h"], d)
-        lstm_in = f16_x if final_ln is None else ws["h"]
-        lstm_split = raw and lang_id is None  # the BiLSTM consumes the raw [hi | lo] hidden states directly
-        if enc is not None:
-            lstm_in = self._lang_proj(enc, enc.shape[1], lang_id, ws, B, T, bilstm)
-        elif final_ln is None and max_label_len is None:
-            if lang_id is not None:
-                lstm_in = self._lang_proj(f16_x, f16_stride, lang_id, ws, B, T, bilstm)
-        elif max_label_len is not None:
-            # REF/model.py:166-174 (training/eval only): fix T to the label length; rare path, torch glue
+        hl = enc
+        if enc is None:
             if final_ln is not None:
-                self._ln(x, final_ln, out_f32=x)
-            mll = int(max_label_len)
-            if mll < T:
-                xs = x[:, :mll].contiguous()
-            else:
-                xs = torch.cat([x, x.new_zeros(B, mll - T, d)], dim=1)
-            ws = self._buffers(B, mll)
-            ws["x"].copy_(xs)
-            x, T, M = ws["x"], mll, B * mll
-            ops.split_f16(x, ws["hl"])
-            if lang_id is not None:
-                lstm_in = self._lang_proj(ws["hl"], 2 * d, lang_id, ws, B, T, bilstm)
-            elif bilstm and raw:
-                lstm_in = ws["hl"]
-            elif bilstm:
-                ws["h"].view(B, T, d).copy_(ws["hl"].view(B, T, 2 * d)[:, :, :d])
-                lstm_in = ws["h"]
-        elif lang_id is not None:
-            self._ln(x, final_ln, out_f16=ws["h"])
-            lstm_in = self._lang_proj(ws["h"], d, lang_id, ws, B, T, bilstm)
-        elif bilstm:
-            self._ln(x, final_ln, out_f16=ws["h"])
-        else:
-            self._ln(x, final_ln, out_f32=x)
+                self._ln(x, final_ln, out_f32=x)  # the encoder's last_hidden_state, fp32
+            fresh = True
+            if max_label_len is not None:
+                # REF/model.py:166-174 (training/eval only): fix T to the label length; rare path, torch glue
+                mll = int(max_label_len)
+                xs = x[:, :mll].contiguous() if mll < T else torch.cat([x, x.new_zeros(B, mll - T, d)], dim=1)
+                ws = self._buffers(B, mll)
+                ws["x"].copy_(xs)
+                x, T, M = ws["x"], mll, B * mll
+            elif self.raw_hidden:
+                fresh = False  # _mel_features already left the split of x in ws["hl"]
+            hl = ws["hl"]
+            if fresh and (lang_id is not None or bilstm):
+                ops.split_f16(x, hl)
+        if lang_id is not None:
+            self._lang_proj(hl, lang_id, ws, B, T)  # -> fp32 x
+            if bilstm:
+                hl = ws["hl"]
+                ops.split_f16(x, hl)
         if bilstm:
             # REF/model.py:182-183: input projection for all steps as one GEMM, then the serial recurrence
-            a_in = lstm_in
             Hs, Hp = self.lstm_h, self.lstm_hp
             y_mid = _v(ws["ctx"], M, 2 * Hp)
             y_last = x if Hp == Hs else ws["ylstm"]
             for layer in range(self.lstm_layers):
                 last = layer == self.lstm_layers - 1
-                if layer == 0 and lstm_split:
-                    ops.gemm(a_in, self.W["lstm0.in.w3"], ws["gx"], n=8 * Hp, slab_k=self.dk, shifts=[0, 0, 0],
+                if layer == 0:
+                    ops.gemm(hl, self.W["lstm0.in.w3"], ws["gx"], n=8 * Hp, slab_k=self.dk, shifts=[0, 0, 0],
                              cols=[0, d, 0], a_rows=M, a_cols=2 * d, a_row_stride=2 * d, m_rows=M, out_row_stride=8 * Hp,
                              bias=self.W["lstm0.in.b"], out_mode=ops.OUT_STORE_F32)
                 else:
-                    self._linear(a_in, f"lstm{layer}.in", ws["gx"], M, d if layer == 0 else 2 * Hp,
-                                 out_mode=ops.OUT_STORE_F32)
+                    ops.gemm(y_mid, self.W[f"lstm{layer}.in.w2"], ws["gx"], n=8 * Hp, slab_k=2 * Hp, shifts=[0, 0],
+                             cols=[0, 0], a_rows=M, a_cols=2 * Hp, a_row_stride=2 * Hp, m_rows=M, out_row_stride=8 * Hp,
+                             bias=self.W[f"lstm{layer}.in.b"], out_mode=ops.OUT_STORE_F32)
                 ops.lstm_layer(ws["gx"], self.W[f"lstm{layer}.whh"], B, T, Hp,
                                y_f16=None if last else y_mid, y_f32=y_last if last else None)
-                a_in = y_mid
             if Hp != Hs:  # drop the padded units of each direction: [fwd Hp | bwd Hp] -> [fwd Hs | bwd Hs] = x
                 ops.gather_cols(ws["ylstm"], x, 2, Hp, Hs)
         for i in range(self.n_conf):
             self._conformer(i, ws, B, T)
-        # tail: dilated stack -> classifier (split precision) + boundary-offset head
+        # tail: dilated stack (split precision, fp32 between the convs) -> classifier (split precision) + offset head
         src = x
-        if self.dil_depth > 0:
-            ops.split_f16(x, ws["hl"])
-            a_in, ars = ws["hl"], 2 * d
-            for i in range(self.dil_depth):
-                last = i == self.dil_depth - 1
-                out = ws["y"] if last else (ws["c"] if i % 2 == 0 else ws["g"])
-                self._conv(a_in, f"dil{i}", out, B, T, d, self.dil_k, 2 ** i, a_row_stride=ars, act=ops.ACT_RELU,
-                           out_mode=ops.OUT_STORE_F32 if last else ops.OUT_STORE_F16)
-                a_in, ars = out, d
+        taps, pad_unit = self.dil_k, (self.dil_k - 1) // 2
+        for i in range(self.dil_depth):
+            ops.split_f16(src, ws["hl"])
+            dil = 2 ** i
+            shifts = [j * dil - pad_unit * dil for j in range(taps) for _ in range(3)]
+            ops.gemm(ws["hl"], self.W[f"dil{i}.w3"], ws["y"], n=d, slab_k=self.dk, shifts=shifts, cols=[0, d, 0] * taps,
+                     a_rows=T, a_cols=2 * d, a_row_stride=2 * d, a_batch_stride=T * 2 * d, batches=B, m_rows=T,
+                     out_row_stride=d, out_batch_stride=T * d, bias=self.W[f"dil{i}.b"], act=ops.ACT_RELU,
+                     out_mode=ops.OUT_STORE_F32)
             src = ws["y"]
         logits, offsets = (ws["logits"], ws["offsets"]) if dest is None else dest
         ops.split_f16(src, ws["hl"])
@@ -653,22 +704,15 @@ class Engine:
         ops.rowdot_sigmoid(ws["c"], self.W["off.w"], self.W["off.b"], offsets)
         return logits[:, :, :self.L], offsets
 
-    def _lang_proj(self, a, a_row_stride, lang_id, ws, B, T, to_f16=False):
-        """REF/model.py:176-180 folded: x = W_h h + (W_e emb[lang] + b), one bias row per batch item.  The result feeds
-        the BiLSTM input GEMM (f16, ws["g"] -- never the buffer it reads: other CTAs still load those rows as their A
-        operand) or becomes the fp32 residual stream (ws["x"])."""
+    def _lang_proj(self, hl, lang_id, ws, B, T):
+        """REF/model.py:176-180 folded: x = W_h h + (W_e emb[lang] + b), one bias row per batch item, in split precision
+        (``hl`` = [hi | lo] of the fp32 hidden state); the result is the new fp32 residual stream ws["x"]."""
         d = self.d
         lang_id = lang_id.to(self.dev).long().view(-1)
         if lang_id.numel() != B:
             raise ValueError("lang_id must have one entry per batch item")
         bias = self.W["lang.bias"].index_select(0, lang_id).contiguous()  # [B, d]
-        out = _v(ws["g"], B * T, d) if to_f16 else ws["x"]
-        if self.raw_hidden:  # a = [hi | lo] of the raw hidden states: x_hi w_hi + x_lo w_hi + x_hi w_lo
-            assert a_row_stride == 2 * d
-            w, slabs = self.W["lang.w3"], dict(shifts=[0, 0, 0], cols=[0, d, 0], a_cols=2 * d)
-        else:
-            w, slabs = self.W["lang.w"], dict(a_cols=d)
-        ops.gemm(a, w, out, n=d, slab_k=self.dk, a_rows=T, a_row_stride=a_row_stride, a_batch_stride=T * a_row_stride,
-                 batches=B, m_rows=T, out_row_stride=d, out_batch_stride=T * d, bias=bias, bias_batch_stride=d,
-                 out_mode=ops.OUT_STORE_F16 if to_f16 else ops.OUT_STORE_F32, **slabs)
-        return out
+        ops.gemm(hl, self.W["lang.w3"], ws["x"], n=d, slab_k=self.dk, shifts=[0, 0, 0], cols=[0, d, 0], a_rows=T,
+                 a_cols=2 * d, a_row_stride=2 * d, a_batch_stride=T * 2 * d, batches=B, m_rows=T, out_row_stride=d,
+                 out_batch_stride=T * d, bias=bias, bias_batch_stride=d, out_mode=ops.OUT_STORE_F32)
+        return ws["x"]

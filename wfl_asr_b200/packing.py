@@ -83,14 +83,21 @@ def interleave_glu(weight2d, bias, tile_n):
     return weight2d[idx].contiguous(), (bias[idx].contiguous() if bias is not None else None)
 
 
-def split_hi_lo(weight2d, k_to=None):
+def split_hi_lo(weight2d, k_to=None, parts="hhl"):
     """fp32 [n, k] -> f16 [n, 3k] = [hi | hi | lo]: pairs with A = [hi | lo] slabs (cols 0, k, 0).  ``k_to``: zero-pad
-    each of the three slabs to this width."""
+    each slab to this width.  ``parts="hl"``: [hi | lo] only (an f16 A operand against split weights, cols 0, 0)."""
     hi = f16(weight2d)
     lo = f16(weight2d.float() - hi.float())
     if k_to is not None:
         hi, lo = pad_k(hi, k_to), pad_k(lo, k_to)
-    return torch.cat([hi, hi, lo], dim=1).contiguous()
+    return torch.cat([hi if p == "h" else lo for p in parts], dim=1).contiguous()
+
+
+def split_hi_lo_taps(weight, in_to):
+    """Conv1d weight fp32 [out, in, k] -> f16 [out, k * 3 * in_to]: per tap the three slabs [hi | hi | lo] (each tap's
+    input channels zero-padded to ``in_to``), pairing with A = [hi | lo] rows shifted by the tap."""
+    o, i, k = weight.shape
+    return torch.cat([split_hi_lo(weight[:, :, j], in_to) for j in range(k)], dim=1).contiguous()
 
 
 def pad_rows(weight2d, rows_to):
