@@ -227,7 +227,12 @@ def _attn_ref(qkv, B, T, H, hd, scale, bias=None):
 
 @pytest.mark.parametrize("hd,H,T,B", [(64, 2, 128, 1), (64, 3, 300, 2), (64, 8, 1500, 1), (256, 2, 200, 2),
                                        (256, 2, 1500, 1), (384, 2, 333, 1), (512, 2, 300, 2), (640, 2, 457, 1),
-                                       (512, 2, 1499, 1), (64, 2, 1, 2), (64, 1, 65, 1), (256, 2, 63, 1), (64, 4, 129, 3)])
+                                       (512, 2, 1499, 1), (64, 2, 1, 2), (64, 1, 65, 1), (256, 2, 63, 1), (64, 4, 129, 3),
+                                       # head_dim 64, 256-row CTAs / 128-key tiles: second query tile empty, partial, full
+                                       (64, 2, 256, 1), (64, 2, 257, 2), (64, 3, 384, 1), (64, 2, 385, 1), (64, 12, 499, 2),
+                                       (64, 16, 799, 1),
+                                       # more 256-row items than SMs, every fourth one without a second query tile
+                                       (64, 16, 799, 16), (64, 8, 640, 40)])
 def test_attention(hd, H, T, B):
     d = H * hd
     qkv = _rand(B, T, 3 * d, seed=23).half()
@@ -236,6 +241,30 @@ def test_attention(hd, H, T, B):
     ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=scale, q_col=0, k_col=d, v_col=2 * d)
     ref = _attn_ref(qkv, B, T, H, hd, scale)
     _report(f"attention hd{hd}", out, ref, 2e-2)
+
+
+@pytest.mark.parametrize("gen", ["v1", "v2"])
+@pytest.mark.parametrize("hd,H,T,B,bias", [(64, 2, 128, 1, False), (64, 3, 300, 2, False), (64, 8, 1500, 1, False), (64, 2, 1, 2, False),
+                                            (64, 1, 65, 1, False), (64, 4, 129, 3, False), (64, 2, 256, 1, False),
+                                            (64, 2, 257, 2, False), (64, 3, 384, 1, False), (64, 2, 385, 1, False),
+                                            (64, 12, 499, 2, True), (64, 16, 799, 4, True), (64, 16, 799, 16, False)])
+def test_attention_hd64_both_generations(monkeypatch, gen, hd, H, T, B, bias):
+    """head_dim 64 has two kernels (attention.cu: 128-row CTAs, 64-key tiles; attention64.cu: persistent 256-row items,
+    128-key tiles) chosen by problem size; WFL_ATTN64 forces each of them over the same edge shapes (second query tile
+    empty / partial / full, one key, items without a second tile inside a multi-item CTA, the WavLM bias)."""
+    monkeypatch.setenv("WFL_ATTN64", gen)
+    d = H * hd
+    qkv = _rand(B, T, 3 * d, seed=123).half()
+    out = torch.full((B, T, d), float("nan"), device=DEV, dtype=torch.float16)
+    scale = hd ** -0.5
+    rel = gate = full_bias = None
+    if bias:
+        rel = _rand(H, 2 * T - 1, seed=124)
+        gate = (1.0 + 0.3 * _rand(B, H, T, seed=125)).contiguous()
+        idx = torch.arange(T, device=DEV)[None, :] - torch.arange(T, device=DEV)[:, None] + T - 1
+        full_bias = gate[..., None] * rel[:, idx][None]
+    ops.attention(qkv, out, B=B, T=T, H=H, hd=hd, scale=scale, q_col=0, k_col=d, v_col=2 * d, rel_bias=rel, gate=gate)
+    _report(f"attention hd64 {gen}", out, _attn_ref(qkv, B, T, H, hd, scale, bias=full_bias), 2e-2)
 
 
 @pytest.mark.parametrize("bias", [False, True])

@@ -31,6 +31,9 @@ namespace wfl {
 int attention_big_dispatch(const void* qkv, int64_t row_stride, int64_t batch_stride, int q_col, int k_col, int v_col,
                            int B, int T, int H, int hd, float scale, void* out, int64_t out_row_stride,
                            int64_t out_batch_stride, cudaStream_t stream);  // attention_big.cu
+int attention64_dispatch(const void* qkv, int64_t row_stride, int64_t batch_stride, int q_col, int k_col, int v_col, int B,
+                         int T, int H, float scale, const float* rel_bias, const float* gate, void* out,
+                         int64_t out_row_stride, int64_t out_batch_stride, cudaStream_t stream);  // attention64.cu
 
 // P (the f16 probabilities) is handed to the tensor core through TMEM, overlaying the S tile it was computed from
 // (tcgen05.st by the softmax warps, A-from-TMEM MMA).  At hd 64 the kernel was shared-memory-bandwidth bound: per
@@ -523,6 +526,19 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
   p.scale_log2 = scale * kLog2e;
   p.rel_bias = rel_bias;
   p.gate = gate;
+  // head_dim 64 without the WavLM bias, with at least one 256-row item per SM: the persistent second-generation kernel
+  // (attention64.cu; measured 0.247 ms against 0.254 at B 32 x H 8 x T 1500, 0.93 against 0.97 at B 64 x H 12).  Small
+  // problems keep the first generation's 128-row CTAs (twice the CTAs to spread over the SMs: 29 us against 46 at
+  // B 1 x H 12 x T 499), and so does the bias variant (in attention64 both threads of a row would evaluate the bias of
+  // all 128 columns: 0.38 ms against 0.22 at B 16 x H 16 x T 799).  WFL_ATTN64=v1|v2 forces one (A/B runs, tests).
+  if (hd == 64) {
+    const char* force = getenv("WFL_ATTN64");
+    const int items = B * H * ((T + 255) / 256);
+    const bool v2 = force != nullptr ? (force[0] == 'v' && force[1] == '2') : (rel_bias == nullptr && items >= num_sms());
+    if (v2)
+      return attention64_dispatch(qkv, row_stride, batch_stride, q_col, k_col, v_col, B, T, H, scale, rel_bias, gate,
+                                  out, out_row_stride, out_batch_stride, stream);
+  }
   switch (hd) {
     case 64:
       if (rel_bias != nullptr)
