@@ -191,6 +191,13 @@ def run_ours(args, rank, world, local_rank):
     del dev_sets, host_sets, labeler, model
     torch.cuda.empty_cache()
     bulk = None if args.no_bulk else run_bulk(args, rank, world, dev)
+    ingest = None
+    if world == 1 and not args.no_ingest:
+        # does the real-audio ingest keep up?  WAV files on tmpfs -> pinned staging -> H2D ->
+        # device PCM decode + peak normalisation (ingest_only), and the same files through infer.infer_folder to .lab
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ingest_bench
+        ingest = ingest_bench.measure(files=args.ingest_files, seconds=wl["seconds"], workers=8, workload=WORKLOAD, dev=dev)
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -268,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "latency_p50_ms": {"value": round(lat_p50, 3), "what": "one 30 s clip, batch 1, pinned host waveform -> python "
                            "segments (H2D + forward + post-processing + D2H), median of 20 synchronous calls"},
-        "bulk": bulk,
+        "bulk": bulk, "ingest": ingest,
     }
     return line
 
@@ -422,6 +429,8 @@ def main():
                     "--impl reference, 8 for the cpu_baseline leg of the default run)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bulk", action="store_true", help="skip the ragged-corpus (BASELINE configs[3]) record")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the file-ingest record (N = 1 only)")
+    ap.add_argument("--ingest-files", type=int, default=128)
     ap.add_argument("--bulk-workload", default="cfg4")
     ap.add_argument("--bulk-utts", type=int, default=10000)
     ap.add_argument("--bulk-max-clips", type=int, default=32)

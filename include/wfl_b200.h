@@ -166,6 +166,15 @@ int wfl_lstm_layer(const float* gx, const void* whh_f16, int32_t B, int32_t T, i
 int wfl_peak_normalize(const double* in, const int64_t* clip_begin, int32_t n_clips, float* out,
                        int64_t out_stride, double* out_f64, double* scratch_max, void* stream);
 
+/* ---- ingest: interleaved PCM frames -> float64 mono on the device (REF/infer.py:217-219: soundfile.read returns
+ * int16 / 32768 resp. int32 / 2^31 resp. the float32 samples as float64; stereo is averaged).  The host copies the
+ * file's data chunk into pinned memory and nothing else. ----
+ */
+#define WFL_PCM_S16 16
+#define WFL_PCM_S32 32
+#define WFL_PCM_F32 3
+int wfl_pcm_to_f64(const void* pcm, int32_t format, int32_t channels, int64_t n_frames, double* out, void* stream);
+
 /* ---- ingest: sinc resampling to the model rate (REF/infer.py:217-220 -> torchaudio.functional.resample on the
  * float64 waveform: TORCHAUDIO/functional/functional.py _get_sinc_resample_kernel + _apply_sinc_resample_kernel) ----
  * out[f*new + p] = sum_{k < 2*width+orig} bank[k][p] * x[f*orig + k - width] (x = 0 outside [0, n_in)), fp64.

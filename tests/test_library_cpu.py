@@ -194,3 +194,39 @@ def test_model_rejects_shapes_the_reference_cannot_run():
         BIOPhonemeTagger(cfg, labels)
     cfg["model"].update(enable_dilated_conv=False)  # an unused even kernel is not an error
     BIOPhonemeTagger(cfg, labels)
+
+
+def test_wav_header_parser_and_device_formats():
+    """ingest.parse_wav_header: plain PCM, WAVE_FORMAT_EXTENSIBLE, odd-sized chunks before the data chunk, malformed
+    files; ingest.device_pcm_format: which encodings wfl_pcm_to_f64 takes (the rest is decoded on the host)."""
+    import io
+    import struct
+
+    import pytest
+
+    from wfl_asr_b200 import ingest, ops
+
+    def wav(tag, ch, sr, bits, pcm, extra=b"", extensible=False):
+        if extensible:
+            fmt = struct.pack("<HHIIHH", 0xFFFE, ch, sr, sr * ch * bits // 8, ch * bits // 8, bits) + struct.pack("<HHI", 22, bits, 0)
+            fmt += struct.pack("<H", tag) + b"\x00" * 14
+        else:
+            fmt = struct.pack("<HHIIHH", tag, ch, sr, sr * ch * bits // 8, ch * bits // 8, bits)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + extra + b"data" + struct.pack("<I", len(pcm)) + pcm
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    pcm = bytes(range(24))
+    tag, ch, sr, bits, off, size = ingest.parse_wav_header(io.BytesIO(wav(1, 2, 44100, 16, pcm)))
+    assert (tag, ch, sr, bits, size) == (1, 2, 44100, 16, 24) and off == 44
+    odd = b"LIST" + struct.pack("<I", 3) + b"abc\x00"  # odd-sized chunk is followed by a pad byte
+    buf = wav(3, 1, 16000, 32, pcm, extra=odd)
+    tag, ch, sr, bits, off, size = ingest.parse_wav_header(io.BytesIO(buf))
+    assert (tag, ch, sr, bits, size) == (3, 1, 16000, 32, 24) and buf[off:off + size] == pcm
+    tag, *_ = ingest.parse_wav_header(io.BytesIO(wav(1, 1, 8000, 24, pcm, extensible=True)))
+    assert tag == 1
+    for bad in (b"", b"RIFF\x00\x00\x00\x00WAVX", wav(1, 1, 8000, 16, pcm)[:30]):
+        with pytest.raises(ValueError):
+            ingest.parse_wav_header(io.BytesIO(bad))
+    assert ingest.device_pcm_format(1, 16) == ops.PCM_S16 and ingest.device_pcm_format(1, 32) == ops.PCM_S32
+    assert ingest.device_pcm_format(3, 32) == ops.PCM_F32
+    assert ingest.device_pcm_format(1, 24) is None and ingest.device_pcm_format(1, 8) is None and ingest.device_pcm_format(3, 64) is None

@@ -589,3 +589,66 @@ def test_resample_matches_oracle(sr, n):
     assert np.abs(got - want).max() <= 1e-12
     same = torch.from_numpy(x).to(DEV)
     assert ingest.resample(same, 16000, 16000) is same
+
+
+# ----------------------------------------------------------------------------------------- ingest
+@pytest.mark.parametrize("fmt,ch,n", [("s16", 1, 48001), ("s16", 2, 30000), ("s32", 1, 777), ("f32", 3, 5000), ("s16", 1, 1)])
+def test_pcm_to_f64_bit_exact(fmt, ch, n):
+    """Device PCM decode = soundfile.read semantics (int / 2^(bits-1) as float64) + the reference's mono mix-down
+    (numpy mean over channels, REF/infer.py:218-219), bit for bit."""
+    rng = np.random.default_rng(5)
+    if fmt == "s16":
+        raw = rng.integers(-32768, 32768, size=(n, ch), dtype=np.int16)
+        ref = raw.astype(np.float64) / 32768.0
+        code = ops.PCM_S16
+    elif fmt == "s32":
+        raw = rng.integers(-2**31, 2**31, size=(n, ch), dtype=np.int64).astype(np.int32)
+        ref = raw.astype(np.float64) / 2147483648.0
+        code = ops.PCM_S32
+    else:
+        raw = rng.standard_normal((n, ch)).astype(np.float32)
+        ref = raw.astype(np.float64)
+        code = ops.PCM_F32
+    ref = ref.mean(axis=1) if ch > 1 else ref[:, 0]
+    dev_raw = torch.from_numpy(raw.view(np.uint8).reshape(-1).copy()).to(DEV)
+    out = torch.empty(n, dtype=torch.float64, device=DEV)
+    ops.pcm_to_f64(dev_raw, code, ch, n, out)
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_folder_ingest_matches_host_decode(tmp_path):
+    """ingest.FolderIngest (pinned staging, copy stream, device decode; host fallback for 24-bit) yields exactly what
+    infer.read_audio + the mono mix-down give, file by file and in order."""
+    import struct
+
+    from wfl_asr_b200 import infer, ingest
+
+    def write(path, x, sr, bits, ch=1):
+        x = np.clip(x, -1, 1)
+        if bits == 16:
+            pcm = (x * 32767.0).astype("<i2").tobytes()
+        elif bits == 24:
+            v = (x * 8388607.0).astype(np.int32)
+            pcm = b"".join(int(s).to_bytes(3, "little", signed=True) for s in v.reshape(-1))
+        else:
+            pcm = x.astype("<f4").tobytes()
+        tag = 3 if bits == 32 else 1
+        with open(path, "wb") as f:
+            f.write(b"RIFF" + struct.pack("<I", 36 + len(pcm)) + b"WAVEfmt " +
+                    struct.pack("<IHHIIHH", 16, tag, ch, sr, sr * ch * bits // 8, ch * bits // 8, bits))
+            f.write(b"data" + struct.pack("<I", len(pcm)) + pcm)
+
+    rng = np.random.default_rng(9)
+    specs = [("a.wav", 16000, 16, 1, 20000), ("b.wav", 44100, 16, 2, 30011), ("c.wav", 22050, 24, 1, 4000),
+             ("d.wav", 16000, 32, 1, 16001), ("e.wav", 48000, 16, 1, 1)]
+    paths = []
+    for name, sr, bits, ch, n in specs:
+        x = rng.uniform(-0.9, 0.9, size=(n, ch) if ch > 1 else n)
+        write(str(tmp_path / name), x, sr, bits, ch)
+        paths.append(str(tmp_path / name))
+    got = list(ingest.FolderIngest(paths * 3, DEV, infer.read_audio, workers=3, window=4))
+    assert [g[0] for g in got] == paths * 3
+    for (path, audio, sr), (name, want_sr, _, _, n) in zip(got, specs * 3):
+        ref, ref_sr = infer.read_audio(path)
+        assert sr == ref_sr == want_sr and audio.dtype == torch.float64 and audio.shape == (n,)
+        assert np.array_equal(audio.cpu().numpy(), ref)

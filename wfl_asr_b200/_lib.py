@@ -58,6 +58,7 @@ SIGNATURES = {
     "wfl_rowdot_sigmoid": [_P, _I64, _I32, _P, _P, _I32, _P, _P],
     "wfl_peak_normalize": [_P, _P, _I32, _P, _I64, _P, _P, _P],
     "wfl_resample_sinc": [_P, _I64, _I32, _I32, _I32, _P, _P, _I64, _P],
+    "wfl_pcm_to_f64": [_P, _I32, _I32, _I64, _P, _P],
     "wfl_whisper_logmel": [_P, _I64, _I32, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _P],
     "wfl_decode_frames": [_P, _I64, _I32, _I64, _I32, _F, _P, _P],
     "wfl_median_filter": [_P, _P, _P, _I32, _I64, _I32, _P],

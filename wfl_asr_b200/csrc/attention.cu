@@ -526,15 +526,15 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
   p.scale_log2 = scale * kLog2e;
   p.rel_bias = rel_bias;
   p.gate = gate;
-  // head_dim 64 without the WavLM bias, with at least one 256-row item per SM: the persistent second-generation kernel
-  // (attention64.cu; measured 0.247 ms against 0.254 at B 32 x H 8 x T 1500, 0.93 against 0.97 at B 64 x H 12).  Small
-  // problems keep the first generation's 128-row CTAs (twice the CTAs to spread over the SMs: 29 us against 46 at
-  // B 1 x H 12 x T 499), and so does the bias variant (in attention64 both threads of a row would evaluate the bias of
-  // all 128 columns: 0.38 ms against 0.22 at B 16 x H 16 x T 799).  WFL_ATTN64=v1|v2 forces one (A/B runs, tests).
+  // head_dim 64 without the WavLM bias (= the Whisper encoders, T = 1500): the persistent second-generation kernel
+  // (attention64.cu; 0.247 ms against 0.254 at B 32 x H 8 x T 1500, 0.93 against 0.97 at B 64 x H 12).  The choice
+  // must NOT depend on the batch size: the two generations sum in different orders, and a clip labeled alone has to
+  // equal the same clip inside a batch bit for bit.  The bias variant stays with the first
+  // generation (in attention64 both threads of a row would evaluate the bias of all 128 columns: 0.38 ms against 0.22
+  // at B 16 x H 16 x T 799).  WFL_ATTN64=v1|v2 forces one (A/B runs, tests).
   if (hd == 64) {
     const char* force = getenv("WFL_ATTN64");
-    const int items = B * H * ((T + 255) / 256);
-    const bool v2 = force != nullptr ? (force[0] == 'v' && force[1] == '2') : (rel_bias == nullptr && items >= num_sms());
+    const bool v2 = force != nullptr ? (force[0] == 'v' && force[1] == '2') : rel_bias == nullptr;
     if (v2)
       return attention64_dispatch(qkv, row_stride, batch_stride, q_col, k_col, v_col, B, T, H, scale, rel_bias, gate,
                                   out, out_row_stride, out_batch_stride, stream);

@@ -36,7 +36,49 @@ __global__ void __launch_bounds__(256) resample_kernel(const double* __restrict_
   out[j] = acc0 + acc1;
 }
 
+// Interleaved PCM frames -> float64 mono, the values soundfile.read + the reference's mono mix-down produce
+// (REF/infer.py:217-219): int16 / 32768, int32 / 2^31, float32 as is; channels averaged by a sequential fp64 sum
+// divided by the channel count (numpy's mean over a short axis).  The host only copies the file's bytes.
+template <typename T>
+__global__ void __launch_bounds__(256) pcm_to_f64_kernel(const T* __restrict__ pcm, int channels, long long n_frames,
+                                                         double scale, double* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_frames) return;
+  const T* f = pcm + i * channels;
+  double acc = static_cast<double>(f[0]) * scale;
+  for (int c = 1; c < channels; ++c) acc = __dadd_rn(acc, static_cast<double>(f[c]) * scale);
+  out[i] = channels > 1 ? __ddiv_rn(acc, static_cast<double>(channels)) : acc;
+}
+
 }  // namespace wfl
+
+extern "C" int wfl_pcm_to_f64(const void* pcm, int32_t format, int32_t channels, int64_t n_frames, double* out,
+                              void* stream_) {
+  using namespace wfl;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  WFL_CHECK_ARG(pcm && out, "wfl_pcm_to_f64: null pointer");
+  WFL_CHECK_ARG(channels >= 1 && channels <= 64 && n_frames >= 0, "wfl_pcm_to_f64: bad shape");
+  if (n_frames == 0) return WFL_OK;
+  const unsigned grid = static_cast<unsigned>((n_frames + 255) / 256);
+  switch (format) {
+    case WFL_PCM_S16:
+      pcm_to_f64_kernel<int16_t><<<grid, 256, 0, stream>>>(static_cast<const int16_t*>(pcm), channels, n_frames,
+                                                           1.0 / 32768.0, out);
+      break;
+    case WFL_PCM_S32:
+      pcm_to_f64_kernel<int32_t><<<grid, 256, 0, stream>>>(static_cast<const int32_t*>(pcm), channels, n_frames,
+                                                           1.0 / 2147483648.0, out);
+      break;
+    case WFL_PCM_F32:
+      pcm_to_f64_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(pcm), channels, n_frames, 1.0, out);
+      break;
+    default:
+      set_error("wfl_pcm_to_f64: format %d not supported on the device (decode on the host)", format);
+      return WFL_ERR_UNSUPPORTED;
+  }
+  WFL_CUDA(cudaGetLastError());
+  return WFL_OK;
+}
 
 extern "C" int wfl_resample_sinc(const double* x, int64_t n_in, int32_t orig, int32_t new_rate, int32_t width,
                                  const double* bank, double* out, int64_t n_out, void* stream) {

@@ -203,6 +203,7 @@ def _forward_clips(sess, clip_rows, lens, lang_id, batch_clips=32):
         for i, ln in enumerate(lens):
             groups.setdefault(ln, []).append(i)
     logits_out, offsets_out = [None] * len(lens), [None] * len(lens)
+    batched = []
     for ln, members in groups.items():
         for s0 in range(0, len(members), batch_clips):
             idx = members[s0:s0 + batch_clips]
@@ -218,8 +219,12 @@ def _forward_clips(sess, clip_rows, lens, lang_id, batch_clips=32):
                 acc_l, acc_o = model(wave, lt)  # fresh tensors (model.forward clones the engine's views)
             else:  # REF/infer.py:265-276: mean over languages when --lang-id is unset (encoder runs once here)
                 acc_l, acc_o = model.forward_language_mean(wave, lang_ids)
+            batched.append((acc_l, acc_o))
             for j, i in enumerate(idx):
                 logits_out[i], offsets_out[i] = acc_l[j], acc_o[j]
+    if model.encoder_type == "whisper":  # one group in clip order, one frame count: hand the batches back whole
+        return (torch.cat([b[0] for b in batched]) if len(batched) > 1 else batched[0][0],
+                torch.cat([b[1] for b in batched]) if len(batched) > 1 else batched[0][1])
     return logits_out, offsets_out
 
 
@@ -239,12 +244,13 @@ def _prepare_file(sess, audio_path):
 
 
 def _prepare_audio(sess, audio_path, audio, sr, forced):
+    """``audio``: decoded samples (numpy, as soundfile returns them) or an fp64 mono device tensor (ingest.FolderIngest)."""
     dev = sess.device
     if len(audio) == 0:
         raise ValueError(f"{audio_path}: empty audio")
     target_sr = sess.config["data"]["sample_rate"]
     if sr != target_sr:  # REF/infer.py:217-220 (torchaudio.functional.resample on the host) -> csrc/resample.cu
-        audio = ingest.resample(ingest.to_device_mono(audio, dev), sr, target_sr)
+        audio = ingest.resample(audio if torch.is_tensor(audio) else ingest.to_device_mono(audio, dev), sr, target_sr)
         sr = target_sr
     clips, lens, chunked = _normalised_clips(audio, sr, dev)
     if chunked:
@@ -252,7 +258,7 @@ def _prepare_audio(sess, audio_path, audio, sr, forced):
     return dict(path=audio_path, clips=clips, lens=lens, chunked=chunked, forced=forced, sr=sr)
 
 
-def _label_files(sess, files, lang_id, confidence_threshold):
+def _label_files(sess, files, lang_id, confidence_threshold, with_text=False):
     """Forward + post-processing for a list of prepared files in one go (REF/infer.py:246-319 per file): all clips of
     all files share the model batches, one post-processing pass decodes every clip and merges the chunks of each
     file, one D2H copy brings all segment records back.  Returns one segment list per file."""
@@ -281,25 +287,42 @@ def _label_files(sess, files, lang_id, confidence_threshold):
         names = [canonical_to_lang(p, lang_name, sess.merge_map) for p in labeler.phon]
     labeler.set_output_names(names)
     # every clip has the same T for Whisper; WavLM clips differ -> pad to the longest, decode each on its own length
-    T = max(l.shape[0] for l in logits)
     n = len(lens)
-    lg = torch.zeros(n, T, logits[0].shape[-1], device=dev)
-    of = torch.zeros(n, T, 2, device=dev)
-    tl = []
-    for i in range(n):
-        lg[i, :logits[i].shape[0]] = logits[i]
-        of[i, :offsets[i].shape[0]] = offsets[i]
-        tl.append(logits[i].shape[0])
+    if torch.is_tensor(logits):  # Whisper: [n, 1500, L] as the model produced it
+        lg, of = logits, offsets
+        T = lg.shape[1]
+        tl = [T] * n
+    else:
+        T = max(l.shape[0] for l in logits)
+        lg = torch.zeros(n, T, logits[0].shape[-1], device=dev)
+        of = torch.zeros(n, T, 2, device=dev)
+        tl = []
+        for i in range(n):
+            lg[i, :logits[i].shape[0]] = logits[i]
+            of[i, :offsets[i].shape[0]] = offsets[i]
+            tl.append(logits[i].shape[0])
     _, merged, nout, fcb, n_files = labeler.postprocess(
         lg, of, torch.tensor(tl, dtype=torch.int32, device=dev),
         torch.tensor(begins, dtype=torch.int32, device=dev),
         torch.tensor(shifts, dtype=torch.float64, device=dev))  # + 0.0 for single-chunk files: exact in fp64
+    if with_text:
+        return labeler.fetch_with_htk(merged, nout, fcb, n_files, T)
     return labeler.fetch(merged, nout, fcb, n_files, T)
 
 
-def _finish_file(f, segments_pred, output_lab_path):
-    """REF/infer.py:312-328: optional forced-phoneme alignment, .lab output."""
+def _finish_file(f, segments_pred, output_lab_path, quiet=False, lab_text=None):
+    """REF/infer.py:312-328: optional forced-phoneme alignment, .lab output.  ``lab_text``: the .lab text of
+    ``segments_pred`` when the caller already has it (computed for the whole pass on the device)."""
     forced = f["forced"]
+    if forced is None and lab_text is not None and output_lab_path:
+        dir_path = os.path.dirname(output_lab_path)
+        if dir_path:
+            os.makedirs(dir_path, exist_ok=True)
+        with open(output_lab_path, "w", encoding="utf-8") as fh:
+            fh.write(lab_text)
+        if not quiet:
+            print(f"Predictions saved to: {output_lab_path}")
+        return segments_pred
     if forced is not None:
         aligned = align_phoneme_list(segments_pred, forced)
         if "SP" not in forced and "AP" not in forced:
@@ -313,7 +336,8 @@ def _finish_file(f, segments_pred, output_lab_path):
         if dir_path:
             os.makedirs(dir_path, exist_ok=True)
         save_lab(output_lab_path, segments_pred)
-        print(f"Predictions saved to: {output_lab_path}")
+        if not quiet:
+            print(f"Predictions saved to: {output_lab_path}")
     return segments_pred
 
 
@@ -332,22 +356,26 @@ def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_mod
 def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_path: str = "best_model.pt",
                  output_dir: str = "outputs", device: str = "cuda", lang_id: int = None,
                  sample=False, top_k=0, top_p=0.0, temperature=1.0, confidence_threshold=0.0,
-                 files_per_pass: int = 128, decode_workers: int = 8):
+                 files_per_pass: int = 128, decode_workers: int = 8, quiet: bool = False):
     """REF/infer.py:330-357, same files, same .lab outputs and the same per-file printout, but the folder is labeled
     ``files_per_pass`` files at a time: their audio is decoded on a thread pool, and all their clips share the model
-    batches and one post-processing pass (``_label_files``) instead of one batch-1 pass per file."""
+    batches and one post-processing pass (``_label_files``) instead of one batch-1 pass per file.  ``quiet`` drops the
+    reference's per-file / per-segment printout (bulk use)."""
+    import builtins
+    print = (lambda *a, **k: None) if quiet else builtins.print  # noqa: A001
     wav_files = [f for f in os.listdir(folder_path) if f.lower().endswith(".wav")]
     os.makedirs(output_dir, exist_ok=True)
     sess = _Session.get(config_path, checkpoint_path, device)
     results = {}
-    from concurrent.futures import ThreadPoolExecutor
-    with torch.cuda.device(sess.device), ThreadPoolExecutor(max_workers=max(1, decode_workers)) as pool:
+    with torch.cuda.device(sess.device):
         for s0 in range(0, len(wav_files), max(1, files_per_pass)):
             names = wav_files[s0:s0 + max(1, files_per_pass)]
             paths = [str(os.path.join(folder_path, w)) for w in names]
-            decoded = list(pool.map(read_audio, paths))
+            # decode_workers threads read the files into pinned memory; PCM -> float64, resampling and normalisation
+            # run on the device (ingest.FolderIngest)
+            decoded = ingest.FolderIngest(paths, sess.device, read_audio, workers=decode_workers)
             files = []
-            for w, path, (audio, sr) in zip(names, paths, decoded):
+            for w, (path, audio, sr) in zip(names, decoded):
                 print(f"\nInferencing: {w}")
                 forced = None
                 phoneme_txt = path.replace(".wav", ".txt")
@@ -358,10 +386,10 @@ def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_
                             forced.extend(line.strip().split())
                     print(f"Loaded forced phoneme list with {len(forced)} phonemes.")
                 files.append(_prepare_audio(sess, path, audio, sr, forced))
-            per_file = _label_files(sess, files, lang_id, confidence_threshold)
-            for w, f, segs in zip(names, files, per_file):
+            per_file, texts = _label_files(sess, files, lang_id, confidence_threshold, with_text=True)
+            for w, f, segs, text in zip(names, files, per_file, texts):
                 output_lab_path = os.path.join(output_dir, w.replace(".wav", ".lab"))
-                segments = _finish_file(f, segs, str(output_lab_path))
+                segments = _finish_file(f, segs, str(output_lab_path), quiet=quiet, lab_text=text)
                 results[w] = segments
                 print("Predicted segments:")
                 for start, end, ph in segments:

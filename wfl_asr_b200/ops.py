@@ -173,6 +173,16 @@ def resample_sinc(x_f64, orig, new, width, bank, out_f64):
     _count(1)
 
 
+PCM_S16, PCM_S32, PCM_F32 = 16, 32, 3  # include/wfl_b200.h WFL_PCM_*
+
+
+def pcm_to_f64(pcm_bytes, fmt, channels, n_frames, out_f64):
+    """pcm_bytes uint8 device tensor holding ``n_frames`` interleaved frames -> out fp64 [n_frames] (mono)."""
+    rc = _lib.load().wfl_pcm_to_f64(_ptr(pcm_bytes), fmt, channels, n_frames, _ptr(out_f64), _stream())
+    _lib.check(rc, "wfl_pcm_to_f64")
+    _count(1)
+
+
 def logmel_scratch(B, n_mels, device):
     """Scratch buffers of wfl_whisper_logmel: (planes f16, dft fp32 [B,3000,448], logspec fp32, clip max + filter spans)."""
     from .frontend import PLANE_SAMPLES

@@ -269,3 +269,24 @@ class Labeler:
         begins = file_clip_begin.cpu().numpy()
         raw = merged.cpu().numpy().reshape(-1).view(SEG_DTYPE)
         return self._to_python(raw, counts, begins, n_files, stride)
+
+    def fetch_with_htk(self, merged, nout, file_clip_begin, n_files, stride):
+        """``fetch`` plus, per file, the .lab text of its segments (REF/utils.py:76-81): int(t * 1e7) of every record of
+        the pass is computed by ONE wfl_htk_times launch and comes back with the records, instead of one launch and
+        two copies per file."""
+        n_rec = merged.numel() // SEG_DTYPE.itemsize
+        s_h = torch.empty(n_rec, dtype=torch.int64, device=merged.device)
+        e_h = torch.empty(n_rec, dtype=torch.int64, device=merged.device)
+        ops.htk_times(merged, n_rec, s_h, e_h)
+        counts = nout[:n_files].cpu().numpy()
+        begins = file_clip_begin.cpu().numpy()
+        raw = merged.cpu().numpy().reshape(-1).view(SEG_DTYPE)
+        s_h, e_h = s_h.cpu().numpy(), e_h.cpu().numpy()
+        segs = self._to_python(raw, counts, begins, n_files, stride)
+        texts = []
+        for f in range(n_files):
+            base = int(begins[f]) * stride
+            n = int(counts[f])
+            texts.append("".join(f"{a} {b} {seg[2]}\n" for a, b, seg in
+                                 zip(s_h[base:base + n].tolist(), e_h[base:base + n].tolist(), segs[f])))
+        return segs, texts
