@@ -253,6 +253,61 @@ int wfl_merge_segments(const wfl_segment* segs, const int32_t* nseg, int64_t cli
 /* REF/utils.py:76-81 save_lab arithmetic: htk[i] = (int64) trunc(t[i] * 1e7) in fp64. */
 int wfl_htk_times(const wfl_segment* segs, int64_t n, int64_t* start_htk, int64_t* end_htk, void* stream);
 
+/* ==== handle level: the whole labeling model behind six calls =======================
+ * What a non-Python caller binds: build the model from the reference's config values and state_dict
+ * (REF/model.py:55-146; checkpoint keys exactly as torch.save(model.state_dict()) writes them, REF/infer.py:205-208),
+ * then run REF/model.py:148-194 (wfl_forward) and REF/infer.py:293-310 + REF/utils.py:10-74,148-186 (wfl_postprocess).
+ *   wfl_create -> wfl_set_weight x (every state_dict entry, host fp32) -> wfl_finalize -> wfl_set_labels ->
+ *   { wfl_forward, wfl_postprocess } ... -> wfl_destroy
+ * The handle packs / folds the weights (conv taps, BatchNorm fold, GLU interleave, split-precision copies, lang_proj
+ * fold) and owns them plus a workspace arena (sized for config.max_batch at finalize, grown on demand outside stream
+ * capture).  The caller owns every input / output buffer; all work is enqueued on the caller's stream.  Repeated
+ * wfl_forward calls on the same buffers replay a CUDA graph captured on the second call.  One handle per device,
+ * not re-entrant.  Scope: encoder_type whisper (WavLM and the mel front-end stay with the Python engine:
+ * wfl_finalize returns WFL_ERR_UNSUPPORTED). */
+#define WFL_ENCODER_WHISPER 0
+#define WFL_ENCODER_WAVLM 1
+#define WFL_ENCODER_NONE 2
+typedef struct wfl_config {
+  int32_t encoder_type;                  /* WFL_ENCODER_*            (config.yaml model.encoder_type)              */
+  int32_t d, layers, heads, ffn, mels;   /* encoder architecture     (named by model.whisper_model; arch.py table) */
+  int32_t enable_bilstm, bilstm_layers;  /* model.enable_bilstm, model.bilstm_num_layer (REF/model.py:105-111)     */
+  int32_t n_conformer, conformer_heads, conformer_ff_expansion, conformer_kernel; /* REF/model.py:113-124           */
+  int32_t enable_dilated, dilated_depth, dilated_kernel;                          /* REF/model.py:126-133           */
+  int32_t n_labels, n_languages, lang_emb_dim;                                    /* REF/model.py:97-98,135         */
+  int32_t precision_high;                /* 1 = [hi | lo] attention value / output weights   */
+  int32_t max_batch;                     /* workspace sized for this many clips at finalize (0 = on first forward) */
+} wfl_config;
+typedef struct wfl_handle wfl_handle;
+
+int wfl_create(const wfl_config* config, wfl_handle** handle);
+/* One state_dict entry: key as in the checkpoint, host fp32 data, shape[ndim].  The handle keeps its own copy. */
+int wfl_set_weight(wfl_handle* handle, const char* state_dict_key, const float* host_fp32, const int64_t* shape,
+                   int32_t ndim);
+/* Packs the weights onto the device; fails with the missing key's name when the state_dict is incomplete. */
+int wfl_finalize(wfl_handle* handle);
+/* The label list (phonemes.txt order; REF/infer.py:203): needed by wfl_postprocess only. */
+int wfl_set_labels(wfl_handle* handle, const char* const* labels, int32_t n_labels);
+enum wfl_query_what {
+  WFL_QUERY_LOGITS_STRIDE = 0,   /* row stride (floats) of the logits buffer: n_labels rounded up to 8             */
+  WFL_QUERY_FRAMES = 1,          /* frames T produced for a clip of `arg` samples                                   */
+  WFL_QUERY_WORKSPACE_BYTES = 2, /* bytes of the workspace arena                                                    */
+  WFL_QUERY_GRAPHS = 3           /* captured CUDA graphs currently cached                                           */
+};
+int wfl_query(wfl_handle* handle, int32_t what, int64_t arg, int64_t* value);
+/* REF/model.py:148-194: wave fp32 [B][wave_stride] (N valid samples per clip, 16 kHz), lang ids int64 [B] or NULL
+ * (NULL skips lang_proj, REF/model.py:176) -> logits fp32 [B][T][logits_stride] (first n_labels columns valid),
+ * offsets fp32 [B][T][2]. */
+int wfl_forward(wfl_handle* handle, const float* wave_dev, int64_t wave_stride, const int64_t* lang_dev, int32_t B,
+                int32_t N, float* logits_dev, float* offsets_dev, void* stream);
+/* REF/infer.py:293-310: threshold / argmax -> median filter -> BIO runs -> merged segments, one file per clip.
+ * logits as wfl_forward wrote them; frames_per_item int32 [B] (device) or NULL = T for every clip; merge_mode =
+ * WFL_MERGE_*.  segs_dev [B][T] records, nseg_dev [B]. */
+int wfl_postprocess(wfl_handle* handle, const float* logits_dev, const float* offsets_dev,
+                    const int32_t* frames_per_item, int32_t B, int32_t T, float threshold, int32_t median_k,
+                    int32_t merge_mode, wfl_segment* segs_dev, int32_t* nseg_dev, void* stream);
+void wfl_destroy(wfl_handle* handle);
+
 #ifdef __cplusplus
 }
 #endif

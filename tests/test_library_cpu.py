@@ -19,11 +19,13 @@ def test_library_exports_header_symbols():
     from wfl_asr_b200 import _lib
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "wfl_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(wfl_\w+)\s*\(", header, re.M))
-    assert len(declared) >= 15
+    declared = set(re.findall(r"^(?:int|void|const char\*)\s+(wfl_\w+)\s*\(", header, re.M))
+    assert len(declared) >= 22
+    for name in ("wfl_create", "wfl_set_weight", "wfl_finalize", "wfl_forward", "wfl_postprocess", "wfl_destroy"):
+        assert name in declared  # the handle-level surface of SURVEY.md section 8b
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/wfl_b200.h but not exported"
-    bound = set(_lib.SIGNATURES) | set(_lib.NOARG)
+    bound = set(_lib.SIGNATURES) | set(_lib.NOARG) | set(_lib.VOID)
     assert declared <= bound, f"header symbols without a ctypes signature: {declared - bound}"
     assert lib.wfl_abi_version() == 1
 
@@ -41,15 +43,17 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "wfl_b200.h"\n'
-        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(wfl_gemm_desc), offsetof(wfl_gemm_desc, w), '
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %d %d %zu %zu %zu\\n", sizeof(wfl_gemm_desc), offsetof(wfl_gemm_desc, w), '
         'offsetof(wfl_gemm_desc, bias), offsetof(wfl_gemm_desc, out), offsetof(wfl_gemm_desc, tile_n), '
-        'offsetof(wfl_gemm_desc, out_col_group_stride), sizeof(wfl_segment), (int)WFL_MAX_SLABS, (int)WFL_WAVLM_STATS_DOUBLES); return 0; }\n')
+        'offsetof(wfl_gemm_desc, out_col_group_stride), sizeof(wfl_segment), (int)WFL_MAX_SLABS, (int)WFL_WAVLM_STATS_DOUBLES, '
+        'sizeof(wfl_config), offsetof(wfl_config, n_labels), offsetof(wfl_config, max_batch)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     G = _lib.GemmDesc
     want = [ctypes.sizeof(G), G.w.offset, G.bias.offset, G.out.offset, G.tile_n.offset, G.out_col_group_stride.offset,
-            ctypes.sizeof(_lib.Segment), _lib.WFL_MAX_SLABS, ops.WAVLM_STATS_DOUBLES]
+            ctypes.sizeof(_lib.Segment), _lib.WFL_MAX_SLABS, ops.WAVLM_STATS_DOUBLES,
+            ctypes.sizeof(_lib.Config), _lib.Config.n_labels.offset, _lib.Config.max_batch.offset]
     assert got == want, (got, want)
 
 

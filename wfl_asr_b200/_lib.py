@@ -39,6 +39,14 @@ class GemmDesc(_C.Structure):
     ]
 
 
+class Config(_C.Structure):
+    """include/wfl_b200.h wfl_config."""
+    _fields_ = [(n, _C.c_int32) for n in (
+        "encoder_type", "d", "layers", "heads", "ffn", "mels", "enable_bilstm", "bilstm_layers", "n_conformer",
+        "conformer_heads", "conformer_ff_expansion", "conformer_kernel", "enable_dilated", "dilated_depth",
+        "dilated_kernel", "n_labels", "n_languages", "lang_emb_dim", "precision_high", "max_batch")]
+
+
 class Segment(_C.Structure):
     _fields_ = [("start", _C.c_double), ("end", _C.c_double), ("ph", _C.c_int32), ("pad_", _C.c_int32)]
 
@@ -68,8 +76,17 @@ SIGNATURES = {
     "wfl_lstm_layer": [_P, _P, _I32, _I32, _I32, _P, _P, _P],
     "wfl_wavlm_conv0": [_P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _I64, _P, _P],
     "wfl_wavlm_gate": [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    # handle level
+    "wfl_create": [_C.POINTER(Config), _C.POINTER(_P)],
+    "wfl_set_weight": [_P, _C.c_char_p, _P, _C.POINTER(_I64), _I32],
+    "wfl_finalize": [_P],
+    "wfl_set_labels": [_P, _C.POINTER(_C.c_char_p), _I32],
+    "wfl_query": [_P, _I32, _I64, _C.POINTER(_I64)],
+    "wfl_forward": [_P, _P, _I64, _P, _I32, _I32, _P, _P, _P],
+    "wfl_postprocess": [_P, _P, _P, _P, _I32, _I32, _F, _I32, _I32, _P, _P, _P],
 }
 NOARG = {"wfl_abi_version": _C.c_int, "wfl_last_error": _C.c_char_p}
+VOID = {"wfl_destroy": [_P]}  # functions returning void
 
 _lib = None
 
@@ -94,6 +111,10 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = []
         fn.restype = restype
+    for name, argtypes in VOID.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = None
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name, None)
         if fn is None:

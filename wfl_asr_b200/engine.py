@@ -116,7 +116,8 @@ class Engine:
         # tools/precision_attribution.py) for 1-3 % of the FLOPs.
         self.raw_hidden = self.arch["type"] == "none"  # hidden states are raw mel powers: _mel_features leaves the split
         self.W["lang.w3"] = packing.split_hi_lo(w[:, :d].to(self.dev), dk)
-        self._put("lang.bias", sd["lang_emb.weight"].float() @ w[:, d:].T + sd["lang_proj.bias"].float())
+        # (accumulated in fp64 and rounded once, like the C++ packer of the handle API: both give the same fp32 table)
+        self._put("lang.bias", (sd["lang_emb.weight"].double() @ w[:, d:].double().T + sd["lang_proj.bias"].double()).float())
         if m.get("enable_bilstm", True):
             self._pack_bilstm(sd)
         self.n_conf = m.get("num_conformer_layers", 2)
