@@ -188,6 +188,29 @@ def run_ours(args, rank, world, local_rank):
         labeler.label_host(one, lang1)
         lat.append((time.perf_counter() - tt) * 1e3)
     lat_p50 = statistics.median(lat[5:])
+    # the same clip through the handle-level C ABI alone (csrc/handle.cu: wfl_forward + wfl_postprocess, its own CUDA
+    # graph; no engine.py, no Python launch loop): pinned host waveform -> device -> segments on the host
+    lat_native = None
+    if cfg["model"]["encoder_type"] == "whisper":
+        from wfl_asr_b200.native import NativeModel
+        nm = NativeModel(cfg, labels, {k: v.detach().cpu() for k, v in model.state_dict().items()}, dev, max_batch=1)
+        side = torch.cuda.Stream(dev)
+        wave1 = torch.empty(1, one.shape[1], device=dev)
+        out1 = (torch.empty(1, 1500, nm.Lp, device=dev), torch.empty(1, 1500, 2, device=dev))
+        latn = []
+        with torch.cuda.stream(side):
+            for i in range(25):
+                torch.cuda.synchronize()
+                tt = time.perf_counter()
+                wave1.copy_(one, non_blocking=True)
+                nm.forward(wave1, lang1, out=out1)
+                segs, nseg = nm.postprocess(out1[0], out1[1], median_filter=pp["median_filter"], merge_mode=pp["merge_segments"],
+                                            confidence_threshold=pp["confidence_threshold"])
+                n = int(nseg.cpu()[0])
+                rec = segs[0, :max(n, 1)].cpu()
+                latn.append((time.perf_counter() - tt) * 1e3)
+        lat_native = statistics.median(latn[5:])
+        nm.close()
     del dev_sets, host_sets, labeler, model
     torch.cuda.empty_cache()
     bulk = None if args.no_bulk else run_bulk(args, rank, world, dev)
@@ -274,7 +297,9 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": round(ms_e2e / args.steps, 3), "segments_per_step": n_seg / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "latency_p50_ms": {"value": round(lat_p50, 3), "what": "one 30 s clip, batch 1, pinned host waveform -> python "
-                           "segments (H2D + forward + post-processing + D2H), median of 20 synchronous calls"},
+                           "segments (H2D + forward + post-processing + D2H), median of 20 synchronous calls",
+                           "handle_c_abi": None if lat_native is None else round(lat_native, 3),
+                           "handle_c_abi_what": "same clip through wfl_forward + wfl_postprocess of the handle-level C ABI only"},
         "bulk": bulk, "ingest": ingest,
     }
     return line

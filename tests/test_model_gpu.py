@@ -348,7 +348,7 @@ def test_infer_audio_end_to_end(tmp_path, seconds, file_sr):
     _write_wav(str(wav), x, sr=file_sr)
     out_lab = tmp_path / "out" / "clip.lab"
     segs = infer.infer_audio(str(wav), str(tmp_path / "config.yaml"), str(tmp_path / "best_model.pt"), str(out_lab),
-                             device="cuda:0", lang_id=1, confidence_threshold=0.1)
+                             device="cuda:0", lang_id=1, confidence_threshold=0.1, use_cache=False)
     text = out_lab.read_text()
     assert text == "".join(po.lab_lines(segs))
     # oracle chain on the same file
@@ -381,6 +381,46 @@ def test_infer_audio_end_to_end(tmp_path, seconds, file_sr):
     assert n_agree / n_frames >= 0.995
 
 
+def test_wfl_cache_logits_cache(tmp_path):
+    """REF/infer.py:222-232,246-249,278-280 (+ :120-131 for 30 s chunks): logits / offsets are cached beside the audio
+    under .wfl_cache/ with the reference's file names and tensor shapes, and a second call labels from the cache."""
+    from wfl_asr_b200 import infer
+    cfg, labels, sd, _, _ = mfg.case_inputs("whisper_base_cfg2")
+    cfg["output"] = {"save_dir": str(tmp_path)}
+    cfg["postprocess"] = {"median_filter": 3, "merge_segments": "right", "confidence_threshold": 0.1}
+    (tmp_path / "phonemes.txt").write_text("\n".join(labels) + "\n")
+    (tmp_path / "langs.txt").write_text("en,0\nja,1\n")
+    with open(tmp_path / "config.yaml", "w") as f:
+        yaml.safe_dump(cfg, f)
+    torch.save(sd, tmp_path / "best_model.pt")
+    wavs = tmp_path / "w"
+    wavs.mkdir()
+    _write_wav(str(wavs / "short.wav"), to.synth_wave(5, 2.5) * 0.8)
+    _write_wav(str(wavs / "long.wav"), to.synth_wave(6, 31.0) * 0.8)
+    args = (str(tmp_path / "config.yaml"), str(tmp_path / "best_model.pt"))
+    first = {n: infer.infer_audio(str(wavs / n), *args, None, device="cuda:0", lang_id=1, confidence_threshold=0.1)
+             for n in ("short.wav", "long.wav")}
+    cache = wavs / ".wfl_cache"
+    names = sorted(p.name for p in cache.iterdir())
+    assert names == ["long_seg0_lang1_logits.pt", "long_seg0_lang1_offsets.pt", "long_seg1_lang1_logits.pt",
+                     "long_seg1_lang1_offsets.pt", "short_lang1_logits.pt", "short_lang1_offsets.pt"]
+    lg = torch.load(cache / "short_lang1_logits.pt", weights_only=False)
+    of = torch.load(cache / "short_lang1_offsets.pt", weights_only=False)
+    assert tuple(lg.shape) == (1, 1500, len(labels)) and tuple(of.shape) == (1500, 2)  # the reference's shapes
+    # second call: same segments, and it really reads the cache (poison one entry and see the labels change)
+    again = infer.infer_audio(str(wavs / "short.wav"), *args, None, device="cuda:0", lang_id=1, confidence_threshold=0.1)
+    assert again == first["short.wav"]
+    torch.save(torch.zeros_like(lg), cache / "short_lang1_logits.pt")
+    poisoned = infer.infer_audio(str(wavs / "short.wav"), *args, None, device="cuda:0", lang_id=1, confidence_threshold=0.1)
+    assert poisoned != first["short.wav"]
+    fresh = infer.infer_audio(str(wavs / "short.wav"), *args, None, device="cuda:0", lang_id=1, confidence_threshold=0.1,
+                              use_cache=False)
+    assert fresh == first["short.wav"]
+    # the language-mean path caches under the "_avg" suffix
+    infer.infer_audio(str(wavs / "short.wav"), *args, None, device="cuda:0", lang_id=None, confidence_threshold=0.1)
+    assert (cache / "short_avg_logits.pt").exists()
+
+
 @pytest.mark.parametrize("name", ["whisper_base_cfg2", "wavlm_base_plus", "mel_none_full"])
 def test_infer_folder_batched_equals_per_file(tmp_path, name, capsys):
     """infer_folder labels the folder in shared batches; every .lab must equal what infer_audio writes for the same
@@ -406,12 +446,12 @@ def test_infer_folder_batched_equals_per_file(tmp_path, name, capsys):
     for lang in (1, None):
         out_dir = tmp_path / f"out_{lang}"
         got = infer.infer_folder(str(folder), *args, output_dir=str(out_dir), device="cuda:0", lang_id=lang,
-                                 confidence_threshold=0.1, files_per_pass=3)
+                                 confidence_threshold=0.1, files_per_pass=3, use_cache=False)
         assert set(got) == {s[0] for s in specs}
         for fn, _, _ in specs:
             single = tmp_path / f"single_{lang}_{fn}.lab"
             segs = infer.infer_audio(str(folder / fn), *args, str(single), device="cuda:0", lang_id=lang,
-                                     confidence_threshold=0.1)
+                                     confidence_threshold=0.1, use_cache=False)
             assert got[fn] == segs, f"{fn} (lang {lang}) differs between folder and single-file labeling"
             assert (out_dir / fn.replace(".wav", ".lab")).read_text() == single.read_text()
     capsys.readouterr()

@@ -76,7 +76,7 @@ def measure(files=256, seconds=30.0, workers=8, workload="cfg2", dev=None):
             yaml.safe_dump(cfg, f)
         args = (os.path.join(tmp, "config.yaml"), os.path.join(tmp, "best_model.pt"))
         kw = dict(device=str(dev), lang_id=0, confidence_threshold=cfg["postprocess"]["confidence_threshold"],
-                  files_per_pass=64, decode_workers=workers, quiet=True)
+                  files_per_pass=64, decode_workers=workers, quiet=True, use_cache=False)
         infer.infer_folder(wav_dir, *args, output_dir=os.path.join(tmp, "warm"), **kw)
         torch.cuda.synchronize(dev)
         t = time.perf_counter()

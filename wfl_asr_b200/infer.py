@@ -258,7 +258,50 @@ def _prepare_audio(sess, audio_path, audio, sr, forced):
     return dict(path=audio_path, clips=clips, lens=lens, chunked=chunked, forced=forced, sr=sr)
 
 
-def _label_files(sess, files, lang_id, confidence_threshold, with_text=False):
+def _cache_paths(f, lang_id):
+    """REF/infer.py:222-229 (single clip) and :120-126 (30 s chunks): the reference's ``.wfl_cache`` file names, per clip."""
+    base_name = os.path.splitext(os.path.basename(f["path"]))[0]
+    cache_dir = os.path.join(os.path.dirname(f["path"]), ".wfl_cache")
+    lang_suffix = f"_lang{lang_id}" if lang_id is not None else "_avg"
+    if f["chunked"]:
+        return [(os.path.join(cache_dir, f"{base_name}_seg{idx}{lang_suffix}_logits.pt"),
+                 os.path.join(cache_dir, f"{base_name}_seg{idx}{lang_suffix}_offsets.pt")) for idx in range(len(f["lens"]))]
+    return [(os.path.join(cache_dir, f"{base_name}{lang_suffix}_logits.pt"),
+             os.path.join(cache_dir, f"{base_name}{lang_suffix}_offsets.pt"))]
+
+
+def _forward_clips_cached(sess, files, rows, lens, lang_id, quiet):
+    """The reference's logits cache (REF/infer.py:222-232,246-249,278-280 and :120-131,158-161): logits / offsets of a
+    clip are read from ``<audio dir>/.wfl_cache/`` when present, else computed and written there.  Like the reference's,
+    the cache is keyed by file name and language only -- not by checkpoint or config -- so it is the caller's job to
+    clear it when either changes (``use_cache=False`` / WFL_NO_CACHE=1 bypasses it)."""
+    paths = [p for f in files for p in _cache_paths(f, lang_id)]
+    hit = [os.path.exists(p[0]) for p in paths]
+    if not any(hit):
+        logits, offsets = _forward_clips(sess, rows, lens, lang_id)
+    else:
+        miss = [i for i, h in enumerate(hit) if not h]
+        lg_m, of_m = _forward_clips(sess, [rows[i] for i in miss], [lens[i] for i in miss], lang_id) if miss else ([], [])
+        logits, offsets = [None] * len(rows), [None] * len(rows)
+        for k, i in enumerate(miss):
+            logits[i], offsets[i] = lg_m[k], of_m[k]
+        for i, h in enumerate(hit):
+            if h:
+                if not quiet:
+                    print(f"Loaded cached logits for {os.path.basename(paths[i][0])}")
+                lg = torch.load(paths[i][0], map_location=sess.device, weights_only=False)
+                logits[i] = lg.squeeze(0).float()
+                offsets[i] = (torch.load(paths[i][1], map_location=sess.device, weights_only=False).float()
+                              if os.path.exists(paths[i][1]) else torch.zeros(logits[i].shape[0], 2, device=sess.device))
+    for i, h in enumerate(hit):
+        if not h:
+            os.makedirs(os.path.dirname(paths[i][0]), exist_ok=True)
+            torch.save(logits[i].unsqueeze(0).clone(), paths[i][0])  # [1, T, L] like the reference's avg_logits
+            torch.save(offsets[i].clone(), paths[i][1])              # [T, 2]
+    return logits, offsets
+
+
+def _label_files(sess, files, lang_id, confidence_threshold, with_text=False, use_cache=False, quiet=False):
     """Forward + post-processing for a list of prepared files in one go (REF/infer.py:246-319 per file): all clips of
     all files share the model batches, one post-processing pass decodes every clip and merges the chunks of each
     file, one D2H copy brings all segment records back.  Returns one segment list per file."""
@@ -278,7 +321,10 @@ def _label_files(sess, files, lang_id, confidence_threshold, with_text=False):
             shifts.append(t)
             t += ln / f["sr"]
         begins.append(len(rows))
-    logits, offsets = _forward_clips(sess, rows, lens, lang_id)
+    if use_cache and not os.environ.get("WFL_NO_CACHE"):
+        logits, offsets = _forward_clips_cached(sess, files, rows, lens, lang_id, quiet)
+    else:
+        logits, offsets = _forward_clips(sess, rows, lens, lang_id)
 
     labeler = sess.labeler
     labeler.threshold = float(confidence_threshold)
@@ -344,19 +390,20 @@ def _finish_file(f, segments_pred, output_lab_path, quiet=False, lab_text=None):
 def infer_audio(audio_path, config_path="config.yaml", checkpoint_path="best_model.pt",
                 output_lab_path=None, device="cuda", lang_id=None,
                 sample=False, top_k=0, top_p=0.0, temperature=1.0,
-                confidence_threshold=0.0):
-    """REF/infer.py:186-328."""
+                confidence_threshold=0.0, use_cache=True):
+    """REF/infer.py:186-328.  ``use_cache``: the reference's ``.wfl_cache`` logits cache beside the audio file (on, as in
+    the reference; see _forward_clips_cached for its staleness caveat)."""
     sess = _Session.get(config_path, checkpoint_path, device)
     with torch.cuda.device(sess.device):  # every launch below goes to the streams of the session's device (-d cuda:1)
         f = _prepare_file(sess, audio_path)
-        segments_pred = _label_files(sess, [f], lang_id, confidence_threshold)[0]
+        segments_pred = _label_files(sess, [f], lang_id, confidence_threshold, use_cache=use_cache)[0]
         return _finish_file(f, segments_pred, output_lab_path)
 
 
 def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_path: str = "best_model.pt",
                  output_dir: str = "outputs", device: str = "cuda", lang_id: int = None,
                  sample=False, top_k=0, top_p=0.0, temperature=1.0, confidence_threshold=0.0,
-                 files_per_pass: int = 128, decode_workers: int = 8, quiet: bool = False):
+                 files_per_pass: int = 128, decode_workers: int = 8, quiet: bool = False, use_cache: bool = True):
     """REF/infer.py:330-357, same files, same .lab outputs and the same per-file printout, but the folder is labeled
     ``files_per_pass`` files at a time: their audio is decoded on a thread pool, and all their clips share the model
     batches and one post-processing pass (``_label_files``) instead of one batch-1 pass per file.  ``quiet`` drops the
@@ -386,7 +433,8 @@ def infer_folder(folder_path: str, config_path: str = "config.yaml", checkpoint_
                             forced.extend(line.strip().split())
                     print(f"Loaded forced phoneme list with {len(forced)} phonemes.")
                 files.append(_prepare_audio(sess, path, audio, sr, forced))
-            per_file, texts = _label_files(sess, files, lang_id, confidence_threshold, with_text=True)
+            per_file, texts = _label_files(sess, files, lang_id, confidence_threshold, with_text=True, use_cache=use_cache,
+                                           quiet=quiet)
             for w, f, segs, text in zip(names, files, per_file, texts):
                 output_lab_path = os.path.join(output_dir, w.replace(".wav", ".lab"))
                 segments = _finish_file(f, segs, str(output_lab_path), quiet=quiet, lab_text=text)
