@@ -59,19 +59,22 @@ __device__ __forceinline__ void pair_sync(int quarter) {
   asm volatile("bar.sync %0, 64;" ::"r"(quarter + 2) : "memory");
 }
 
-template <int HD, int KV_STAGES, bool kPTmem>
+// KT = keys per tile: 64, or 128 for head dim 256 (S = Q K^T is then an M128 x N128 MMA -- N = 64 runs the tensor pipe
+// at about half rate -- and the per-tile overheads of the softmax warps are amortised over 64 columns per thread)
+template <int HD, int KV_STAGES, bool kPTmem, int KT = 64>
 struct AttnCfg {
   static constexpr int kHdBlocks = HD / 64;
   static constexpr int kQBytes = 128 * HD * 2;
-  static constexpr int kKBytes = kKvTile * HD * 2;
-  static constexpr int kVBytes = kKvTile * HD * 2;
-  static constexpr int kPBytes = kPTmem ? 0 : 128 * kKvTile * 2;
+  static constexpr int kKBytes = KT * HD * 2;
+  static constexpr int kVBytes = KT * HD * 2;
+  static constexpr int kPBytes = kPTmem ? 0 : 128 * KT * 2;
+  static_assert(kPTmem || KT == 64, "the shared-memory P path is written for 64-key tiles");
   static constexpr int kXchgBytes = 2 * 2 * 128 * 4;  // row-max exchange, double-buffered (row sums reuse the idle half)
   static constexpr int kSmemBytes = kQBytes + KV_STAGES * (kKBytes + kVBytes) + 2 * kPBytes + kXchgBytes + 256;
   // S is triple-buffered when TMEM allows: the single MMA-issuing thread is in-order, so with two buffers QK_{j+2}
   // could only be issued after P_j arrived; a third buffer lets it run two tiles ahead of the softmax warps.
-  static constexpr int kSBufs = HD <= 256 ? 3 : 2;
-  static constexpr int kOCol = kSBufs * kKvTile;  // TMEM column where O starts (after the S buffers)
+  static constexpr int kSBufs = KT == 128 ? 2 : (HD <= 256 ? 3 : 2);
+  static constexpr int kOCol = kSBufs * KT;  // TMEM column where O starts (after the S buffers)
   static_assert(kOCol + HD <= 512, "TMEM overflow");
   static constexpr uint32_t kTmemCols = kOCol + HD <= 256 ? 256 : 512;
   static constexpr int kCtasPerSm = (kSmemBytes <= 113 * 1024 && kTmemCols <= 256) ? 2 : 1;
@@ -86,12 +89,13 @@ struct AttnParams {
   const float* gate;      // [B][H][T] or null
 };
 
-template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias>
-__global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES, kPTmem>::kCtasPerSm))
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64>
+__global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES, kPTmem, KT>::kCtasPerSm))
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                  const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
-  using Cfg = AttnCfg<HD, KV_STAGES, kPTmem>;
-  constexpr int KV_TILE = kKvTile;
+  using Cfg = AttnCfg<HD, KV_STAGES, kPTmem, KT>;
+  constexpr int KV_TILE = KT;
+  constexpr int CW = KT / 2;  // score columns per softmax thread (two threads share a query row)
   // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (128B swizzle); checked below
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -289,12 +293,13 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       const int sb = j & 1;         // P / exchange buffer parity
       const int ss = kHasBias ? j % S_BUFS : ss_run;
       const uint32_t ss_phase = kHasBias ? static_cast<uint32_t>((j / S_BUFS) & 1) : ph_run;
-      const int kv0 = j * KV_TILE + ch * 32;  // first key of this warp's columns
+      const int kv0 = j * KV_TILE + ch * CW;  // first key of this warp's columns
       mbar_wait(&s_full[ss], ss_phase);
       tc_fence_after();
 #ifndef WFL_EXP_NOSOFTMAX  // experiment build only: skip the math, keep the barrier protocol
-      uint32_t v[32];
-      tmem_ld32(lane_addr + ss * KV_TILE + ch * 32, v);
+      uint32_t v[CW];
+      if constexpr (CW == 32) tmem_ld32(lane_addr + ss * KV_TILE + ch * CW, v);
+      else tmem_ld64(lane_addr + ss * KV_TILE + ch * CW, v);
       tmem_ld_wait();
 
       // One tile of online softmax.  The scores are brought to ONE form in place in v[] -- raw accumulator bits, to be
@@ -309,19 +314,19 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const float sc = kBias ? 1.0f : p.scale_log2;
         if constexpr (kBias) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < CW; ++i) {
             const int k = min(kv0 + i, p.T - 1);
             v[i] = __float_as_uint(fmaf(gate_l2, __ldg(bias_row + k), __uint_as_float(v[i]) * p.scale_log2));
           }
         }
         if (tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
+          for (int i = 0; i < CW; ++i)
             if (kv0 + i >= p.T) v[i] = 0xff800000u;  // -inf
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(v[i]));
+        for (int i = 0; i < CW; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(v[i]));
         const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sc;
         // combine with the warp that owns the other 32 columns of these rows
         float* xm = xmax + (sb * 2) * 128;
@@ -364,9 +369,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // register limit and keeps four scalar partial sums (the packed form spills there)
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
         uint64_t sum2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
-        uint32_t pk[16];
+        uint32_t pk[CW / 2];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
+        for (int i = 0; i < CW; i += 2) {
           float a0, a1;
           upk2(fma2(pk2u(v[i], v[i + 1]), sc2, negm2), a0, a1);  // one FFMA2 for the pair
           const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);
@@ -385,10 +390,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           // this warp's 32 keys = 16 packed columns of the P tile that overlays S buffer ss (both warps of the pair
           // finished reading S before pair_sync above, so the overlay is safe)
 #ifndef WFL_EXP_NOSTORE
-          tmem_st16(lane_addr + ss * KV_TILE + ch * 16, pk);
+          if constexpr (CW == 32) tmem_st16(lane_addr + ss * KV_TILE + ch * 16, pk);
+          else tmem_st32(lane_addr + ss * KV_TILE + ch * 32, pk);
           tmem_st_wait();
 #else
-          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) tmem_st16(lane_addr + ss * KV_TILE + ch * 16, pk);
+          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) tmem_st16(lane_addr + ss * KV_TILE + ch * 16, reinterpret_cast<uint32_t(&)[16]>(pk));
 #endif
         } else {
           uint8_t* p_row = p_smem + sb * Cfg::kPBytes + r * 128;
@@ -460,17 +466,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 }
 
-template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias>
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64>
 static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int B, int T, int H,
                             const AttnParams& p, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                             cudaStream_t stream) {
-  using Cfg = AttnCfg<HD, KV_STAGES, kPTmem>;
+  using Cfg = AttnCfg<HD, KV_STAGES, kPTmem, KT>;
   CUtensorMap mq, mkv, mo;
   {
     uint64_t dims[3] = {(uint64_t)row_stride, (uint64_t)T, (uint64_t)B};  // any column of the row may be addressed
     uint64_t strides[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
     uint32_t box_q[3] = {64, 128, 1};
-    uint32_t box_kv[3] = {64, (uint32_t)kKvTile, 1};
+    uint32_t box_kv[3] = {64, (uint32_t)KT, 1};
     int rc = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, qkv, dims, strides, box_q,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -486,7 +492,7 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias>;
+  auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias, KT>;
   static PerDeviceOnce configured;  // per instantiation and device
   if (configured.needed()) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -548,8 +554,14 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
                                                   out_batch_stride, stream);
     case 256:
       if (rel_bias != nullptr) break;
+      // WFL_ATTN256_KT128=1: 128-key tiles (full-rate M128 x N128 score MMAs).  Shared memory then holds only ONE K and
+      // one V stage beside Q (64 KB each), the loads no longer overlap the products, and it measures 0.193 ms against
+      // 0.168 ms for 64-key tiles with two stages (B 32, H 2, T 1500) -- kept as a build for that comparison only.
+      if (getenv("WFL_ATTN256_KT128") != nullptr)
+        return launch_attention<256, 1, true, false, 128>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+                                                          out_batch_stride, stream);
       return launch_attention<256, 2, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
-                                            out_batch_stride, stream);
+                                                   out_batch_stride, stream);
     case 384:
       if (rel_bias != nullptr) break;
       return launch_attention<384, 1, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
