@@ -240,6 +240,9 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         tc_fence_after();
         const uint32_t k_addr = k_addr0 + stage * kA64KvBytes;
         const uint32_t q_addr = q_addr0 + buf * 2 * kA64QTile;
+#ifdef WFL_A64_NOQK  // ablation build: barriers only
+        if (false)
+#endif
 #pragma unroll
         for (int k16 = 0; k16 < 4; ++k16) {
           const uint64_t da = umma_smem_desc(q_addr + k16 * 32, 16, 1024);
@@ -309,6 +312,9 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             // the first product of an item overwrites O: the previous item's epilogue must have read it
             if (j == 0 && sub == 0 && m > 0) MMA_WAIT(&o_free[qt], (m - 1) & 1);
             tc_fence_after();
+#ifdef WFL_A64_NOPV  // ablation build: barriers only
+            if (false)
+#endif
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const int k16 = (kk >> 1) * 4 + sub * 2 + (kk & 1);  // 16-key step inside the tile
@@ -338,7 +344,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t s_addr = lane_addr + kA64ColS + qt * 128 + half * 64;
-    const uint32_t s_addr_other = lane_addr + kA64ColS + qt * 128 + (half ^ 1) * 64;
+
     const uint32_t p_addr = lane_addr + kA64ColP + qt * 64 + half * 32;
     const uint32_t o_addr = lane_addr + kA64ColO + qt * 64 + half * 32;
     // Scores are brought to one form in registers: value * sc is the base-2 exponent.
@@ -372,65 +378,77 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         mbar_wait(&s_full[qt], g & 1);
         A64_TRACE(1);
         tc_fence_after();
-        // Row maximum over ALL 128 columns, computed by BOTH threads of the row: the other thread's 64 columns are
-        // streamed through 32 registers first (TMEM reads are nearly free: 16 TB/s per SM), then this thread's own
-        // 64 columns are loaded to stay.  No exchange of maxima through shared memory and no named barrier per tile
-        // -- the two warps that share a row quarter (and an SM sub-partition) are no longer locked in step, so one
-        // warp's barrier / TMEM latencies hide behind the other's exponentials.  Both threads derive the same m_tile
-        // from the same data, so their rescale decisions agree.
-        float mx[2] = {-INFINITY, -INFINITY};
-        const int kv_other = j * kA64Kv + (half ^ 1) * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t w[32];
-          tmem_ld32(s_addr_other + c * 32, w);
+        // The ablation builds (tools/build_variant.py -DWFL_A64_NOEXP/-NOPV/-NOQK) show what bounds this kernel: without
+        // ANY exponential or MMA it still takes 0.19 of its 0.25 ms -- the serial chain of one tile in a softmax warp
+        // (barrier round trips, TMEM loads, row max, P stores), which the warps of a query tile walk in step.  So
+        // the chain is kept short: the exponentials of the first 32 keys start right after the load, against the
+        // offset of the tiles before (speculation); the row maximum of THIS tile is computed beside them, exchanged
+        // with the other column half, and only has to confirm that no row outgrew the offset by more than 2^8
+        // before P is published.  If one did (rare after an item's first tile), O is rescaled and the tile redone
+        // from S, which is handed back to the tensor core only after that decision.
+        uint32_t v[64];
+        auto load_scores = [&]() {
+          tmem_ld64(s_addr, v);
           tmem_ld_wait();
           if constexpr (kHasBias) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int k = min(kv_other + c * 32 + i, p.T - 1);
-              w[i] = __float_as_uint(fmaf(gate_l2, __ldg(bias_row + k), __uint_as_float(w[i]) * p.scale_log2));
+            for (int i = 0; i < 64; ++i) {
+              const int k = min(kv0 + i, p.T - 1);
+              v[i] = __float_as_uint(fmaf(gate_l2, __ldg(bias_row + k), __uint_as_float(v[i]) * p.scale_log2));
             }
           }
           if (tail) {
-            const int valid = p.T - (kv_other + c * 32);
+            const int valid = p.T - kv0;  // keys of these 64 columns inside the sequence (compared with immediates)
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i >= valid) w[i] = 0xff800000u;
+            for (int i = 0; i < 64; ++i)
+              if (i >= valid) v[i] = 0xff800000u;  // -inf
           }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mx[(i >> 1) & 1] = fmax3(mx[(i >> 1) & 1], __uint_as_float(w[i]), __uint_as_float(w[i + 1]));
-        }
-        uint32_t v[64];
-        tmem_ld64(s_addr, v);
-        tmem_ld_wait();
+        };
+        load_scores();
         A64_TRACE(2);
-        // every score this thread needs is in registers: S_qt goes back to the tensor core (Q K^T of the next tile)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[qt]);
-
-        if constexpr (kHasBias) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const int k = min(kv0 + i, p.T - 1);
-            v[i] = __float_as_uint(fmaf(gate_l2, __ldg(bias_row + k), __uint_as_float(v[i]) * p.scale_log2));
-          }
-        }
-        if (tail) {
-          const int valid = p.T - kv0;  // keys of these 64 columns inside the sequence (compared with immediates)
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= valid) v[i] = 0xff800000u;  // -inf
-        }
+        float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int i = 0; i < 64; i += 2)
           mx[(i >> 1) & 1] = fmax3(mx[(i >> 1) & 1], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-        const float m_tile = fmaxf(mx[0], mx[1]) * sc;
+        const float m_half = fmaxf(mx[0], mx[1]) * sc;
+        float* xm = xmax + ((qt * 2 + (g & 1)) * 2) * 128;
+        xm[half * 128 + r] = m_half;
+
+        uint64_t sum2[2];
+        // exponentials of sub-block `sub` (32 keys), packed IN PLACE (v[i], v[i+1] -> v[i/2]): the store wants
+        // consecutive registers, and a second block beside the 64 scores does not fit 96 registers per thread
+        auto exps = [&](int sub) {
+          const float neg_m = -m_used;
+          const uint64_t sc2 = pk2(sc, sc), negm2 = pk2(neg_m, neg_m);
+#pragma unroll
+          for (int ii = 0; ii < 32; ii += 2) {
+            const int i = sub * 32 + ii;
+            const uint64_t a2 = fma2(pk2u(v[i], v[i + 1]), sc2, negm2);
+            float e0, e1;
+            if (WFL_A64_POLY_EVERY > 0 && ((i >> 1) % (WFL_A64_POLY_EVERY > 0 ? WFL_A64_POLY_EVERY : 1)) == WFL_A64_POLY_EVERY - 1) {
+              ex2_poly2(a2, e0, e1);
+            } else {
+              float a0, a1;
+              upk2(a2, a0, a1);
+#ifdef WFL_A64_NOEXP  // ablation build: no MUFU work
+              e0 = fmaf(a0, 1e-3f, 1.0f);
+              e1 = fmaf(a1, 1e-3f, 1.0f);
+#else
+              e0 = ex2_ftz(a0);
+              e1 = ex2_ftz(a1);
+#endif
+            }
+            sum2[(i >> 1) & 1] = add2(sum2[(i >> 1) & 1], pk2(e0, e1));
+            v[i >> 1] = pack_f16(e0, e1);
+          }
+        };
+        sum2[0] = sum2[1] = pk2(0.f, 0.f);
+        if (j > 0) exps(0);  // speculative: against the offset of the tiles before
+        pair_sync();
         A64_TRACE(3);
+        const float m_tile = fmaxf(m_half, xm[(half ^ 1) * 128 + r]);
         const float m_new = fmaxf(m_used, m_tile);
-        const bool grow = m_new > m_used + kA64Rescale;  // also true on the first tile (m_used = -inf)
+        const bool grow = m_new > m_used + kA64Rescale;  // always true on an item's first tile (m_used = -inf)
         if (__any_sync(0xffffffffu, grow)) {  // identical decision in both warps of the pair (same rows, same values)
           if (j > 0) {
             // O must be quiescent: every P V of the previous tile has retired
@@ -444,45 +462,34 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
             tmem_st32(o_addr, o);
             l_sum *= factor;
+            load_scores();  // the speculative pass packed over the first 32 scores
           }
           m_used = m_new;
+          sum2[0] = sum2[1] = pk2(0.f, 0.f);
+          exps(0);
         }
-        const float neg_m = -m_used;
-        const uint64_t sc2 = pk2(sc, sc), negm2 = pk2(neg_m, neg_m);
-        uint64_t sum2[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
-        // P is packed IN PLACE (v[i], v[i+1] -> v[i/2]) and leaves in two sub-blocks of 32 keys: the tensor core
-        // multiplies sub-block 0 by V while this thread exponentiates sub-block 1
+        // the scores are no longer needed in tensor memory: S_qt goes back to the tensor core (Q K^T of the next tile)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[qt]);
+        // P_qt is single-buffered: the P V products of the previous tile must have retired before it is overwritten.
+        // ONE wait covers both sub-blocks (they are issued in order by one thread, and a commit arrives only when every
+        // earlier MMA of that thread has completed); sub-block 1 was issued half a tile of exponentials ago.
+        if (g > 0) {
+          mbar_wait(&pv_done[qt * 2 + 1], (g - 1) & 1);
+          tc_fence_after();
+        }
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
-#pragma unroll
-          for (int i = sub * 32; i < sub * 32 + 32; i += 2) {
-            const uint64_t a2 = fma2(pk2u(v[i], v[i + 1]), sc2, negm2);
-            float e0, e1;
-            if (WFL_A64_POLY_EVERY > 0 && ((i >> 1) % (WFL_A64_POLY_EVERY > 0 ? WFL_A64_POLY_EVERY : 1)) == WFL_A64_POLY_EVERY - 1) {
-              ex2_poly2(a2, e0, e1);
-            } else {
-              float a0, a1;
-              upk2(a2, a0, a1);
-              e0 = ex2_ftz(a0);
-              e1 = ex2_ftz(a1);
-            }
-            sum2[(i >> 1) & 1] = add2(sum2[(i >> 1) & 1], pk2(e0, e1));
-            v[i >> 1] = pack_f16(e0, e1);
-          }
+          if (sub == 1) exps(1);
           A64_TRACE(4 + sub * 2);
-          // this sub-block of P_qt is single-buffered: its P V of the previous tile must have retired (it was issued
-          // half a tile of exponentials ago)
-          if (g > 0) {
-            mbar_wait(&pv_done[qt * 2 + sub], (g - 1) & 1);
-            tc_fence_after();
-          }
-          A64_TRACE(5 + sub * 2);
           if (sub == 0) tmem_st16_of64<0>(p_addr, v);
           else tmem_st16_of64<16>(p_addr + 16, v);
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[qt * 2 + sub]);
+          A64_TRACE(5 + sub * 2);
         }
         float s0, s1, s2, s3;
         upk2(sum2[0], s0, s1);
