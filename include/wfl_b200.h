@@ -253,6 +253,20 @@ int wfl_merge_segments(const wfl_segment* segs, const int32_t* nseg, int64_t cli
 /* REF/utils.py:76-81 save_lab arithmetic: htk[i] = (int64) trunc(t[i] * 1e7) in fp64. */
 int wfl_htk_times(const wfl_segment* segs, int64_t n, int64_t* start_htk, int64_t* end_htk, void* stream);
 
+/* ---- DSP boundary detector of the label corrector (REF/correct_label.py:15-37; librosa 0.11 on the host there) ----
+ * wfl_stft_mag: |STFT| (power 1) or |STFT|^2 (power 2) of y fp32 [n]: frames = 1 + n / hop, centred with zero padding,
+ * periodic Hann window of n_fft (512 or 2048) samples; out fp32 [frames][n_fft / 2 + 1].
+ * wfl_spectral_flux: flux[0] = flux[frames] = 0, flux[t] = || S[t] - S[t-1] ||_2 (np.pad(sqrt(sum(diff(S)^2)), 1)).
+ * wfl_mfcc_delta_mag: P = power spectrogram [frames][bins]; mel_fb fp32 [n_mels][bins] with the non-zero bin span
+ * [mel_span[2m], mel_span[2m+1]) of every filter; dB = 10 log10(max(1e-10, mel)) floored at max - 80; mfcc = dct
+ * [n_mfcc][n_mels] applied per frame; delta_mag[t] = mean_c |Savitzky-Golay slope (9 frames, order 1, "interp" edges)|.
+ * scratch_db fp32 [frames][n_mels], scratch_mfcc fp32 [frames][n_mfcc], scratch_max one uint32. */
+int wfl_stft_mag(const float* y, int64_t n, int32_t n_fft, int32_t hop, int32_t power, float* out, void* stream);
+int wfl_spectral_flux(const float* S, int32_t frames, int32_t bins, float* flux, void* stream);
+int wfl_mfcc_delta_mag(const float* P, int32_t frames, int32_t bins, const float* mel_fb, const int32_t* mel_span,
+                       int32_t n_mels, const float* dct, int32_t n_mfcc, float* scratch_db, float* scratch_mfcc,
+                       uint32_t* scratch_max, float* delta_mag, void* stream);
+
 /* ==== handle level: the whole labeling model behind six calls =======================
  * What a non-Python caller binds: build the model from the reference's config values and state_dict
  * (REF/model.py:55-146; checkpoint keys exactly as torch.save(model.state_dict()) writes them, REF/infer.py:205-208),

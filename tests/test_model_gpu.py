@@ -638,3 +638,31 @@ def test_encoder_run_to_run_determinism_soak():
             bad = (l != first[0]).flatten(1).any(dim=1).nonzero().flatten().tolist()
             assert not bad, f"pass {r} differs from pass 0 in clips {bad}"
             assert torch.equal(o, first[1])
+
+
+def test_correct_label_process_file_end_to_end(tmp_path):
+    """correct_label.process_file (REF/correct_label.py:157-184): wav + .lab -> boundaries detected on the GPU -> snapped
+    .lab, against the oracle chain (restated detector + the reference-pinned snapping), including the pre-made
+    ``_boundary.txt`` path and its clean-up."""
+    from oracle import correct_label_oracle as co
+    from wfl_asr_b200 import correct_label as cl
+    y = (to.synth_wave(91, 6.0) * 0.8)
+    y[30000:31000] *= 0.02
+    wav = tmp_path / "utt.wav"
+    _write_wav(str(wav), y)
+    pcm = (np.clip(y, -1, 1) * 32767.0).astype("<i2").astype(np.float32) / 32768.0  # what the file holds
+    lab_in = "0 9000000 a\n9000000 19500000 b\n19500000 41000000 c\n41000000 60000000 d\n"
+    (tmp_path / "utt.lab").write_text(lab_in)
+    cl.process_file(str(wav))
+    want_pred, *_ = co.detect_boundaries(pcm, 16000)
+    segs = [(float(a) / 1e7, float(b) / 1e7, c) for a, b, c in (ln.split() for ln in lab_in.splitlines())]
+    want = "".join(f"{int(s * 1e7)} {int(e * 1e7)} {l}\n" for s, e, l in co.snap_segments(segs, want_pred))
+    got = (tmp_path / "utt.lab").read_text()
+    assert got == want and got != lab_in and not (tmp_path / "utt_boundary.txt").exists()
+    # a pre-made boundary file is used instead of the detector, then removed
+    (tmp_path / "utt.lab").write_text(lab_in)
+    (tmp_path / "utt_boundary.txt").write_text("0.910000\n1.940000\n")
+    cl.process_file(str(wav))
+    # each predicted boundary is used once (REF/correct_label.py:48,66,79): a's end takes 0.91, so b's start stays
+    assert (tmp_path / "utt.lab").read_text() == "0 9100000 a\n9000000 19400000 b\n19500000 41000000 c\n41000000 60000000 d\n"
+    assert not (tmp_path / "utt_boundary.txt").exists()

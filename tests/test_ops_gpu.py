@@ -652,3 +652,38 @@ def test_folder_ingest_matches_host_decode(tmp_path):
         ref, ref_sr = infer.read_audio(path)
         assert sr == ref_sr == want_sr and audio.dtype == torch.float64 and audio.shape == (n,)
         assert np.array_equal(audio.cpu().numpy(), ref)
+
+
+# ----------------------------------------------------------------------------------------- DSP boundary detector
+@pytest.mark.parametrize("n_fft,power,n", [(512, 1, 16000), (2048, 2, 16000), (512, 1, 4801), (2048, 2, 1500), (512, 1, 159)])
+def test_stft_mag_matches_oracle(n_fft, power, n):
+    from oracle import correct_label_oracle as co
+    y = (to.synth_wave(41, 3.0)[:n]).astype(np.float32)
+    ref = co.stft_mag(y, n_fft, 160).T.astype(np.float64)  # [frames, bins]
+    if power == 2:
+        ref = ref ** 2
+    out = torch.full((1 + n // 160, n_fft // 2 + 1), float("nan"), device=DEV)
+    ops.stft_mag(torch.from_numpy(y).to(DEV), n_fft, 160, power, out)
+    assert tuple(out.shape) == ref.shape
+    _report(f"stft {n_fft}", out, torch.from_numpy(ref).to(DEV), 2e-5)
+
+
+@pytest.mark.parametrize("seconds", [0.5, 3.0, 12.3])
+def test_boundary_features_and_peaks_match_oracle(seconds):
+    """REF/correct_label.py:15-37 on the device against the numpy/scipy restatement of librosa's algorithms
+    (oracle/correct_label_oracle.py -- unpinned: librosa itself is not installed here): the two per-frame curves within
+    1e-3 of their unit scale, and the detected boundaries identical (a frame may only differ where the combined curve
+    has a near-tie)."""
+    from oracle import correct_label_oracle as co
+    from wfl_asr_b200 import correct_label as cl
+    y = to.synth_wave(55, seconds).astype(np.float32)
+    y[len(y) // 3:len(y) // 3 + 800] *= 0.05  # a quiet gap: sharp onsets for the detector
+    flux, dmag = cl.boundary_features(y, 16000)
+    ref_flux, ref_dmag = co.features(y, 16000)
+    assert flux.shape == ref_flux.shape and dmag.shape == ref_dmag.shape
+    assert np.abs(flux - ref_flux).max() <= 1e-3 and np.abs(dmag - ref_dmag).max() <= 1e-3
+    got, *_ = cl.detect_boundaries(y, 16000)
+    want, *_ = co.detect_boundaries(y, 16000)
+    common = len(set(got) & set(want))
+    print(f"[boundaries {seconds}s] {len(got)} detected, {len(want)} by the oracle, {common} identical")
+    assert len(want) > 0 and common >= 0.98 * max(len(got), len(want))

@@ -76,6 +76,9 @@ SIGNATURES = {
     "wfl_lstm_layer": [_P, _P, _I32, _I32, _I32, _P, _P, _P],
     "wfl_wavlm_conv0": [_P, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _I64, _P, _P],
     "wfl_wavlm_gate": [_P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P],
+    "wfl_stft_mag": [_P, _I64, _I32, _I32, _I32, _P, _P],
+    "wfl_spectral_flux": [_P, _I32, _I32, _P, _P],
+    "wfl_mfcc_delta_mag": [_P, _I32, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _P],
     # handle level
     "wfl_create": [_C.POINTER(Config), _C.POINTER(_P)],
     "wfl_set_weight": [_P, _C.c_char_p, _P, _C.POINTER(_I64), _I32],

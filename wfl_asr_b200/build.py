@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libwfl_b200.so")
 STAMP = os.path.join(PKG_DIR, ".libwfl_b200.stamp")
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention64.cu", "attention_big.cu", "rowops.cu", "logmel.cu", "postproc.cu", "lstm.cu", "wavlm.cu", "resample.cu", "handle.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention64.cu", "attention_big.cu", "rowops.cu", "logmel.cu", "postproc.cu", "lstm.cu", "wavlm.cu", "resample.cu", "handle.cu", "boundary.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--compiler-options", "-fPIC", "-cudart", "shared"]
 

@@ -183,6 +183,32 @@ def pcm_to_f64(pcm_bytes, fmt, channels, n_frames, out_f64):
     _count(1)
 
 
+def stft_mag(y, n_fft, hop, power, out):
+    """y fp32 [n] -> out fp32 [1 + n // hop, n_fft // 2 + 1] (|STFT| or |STFT|^2, centred, zero padded, periodic Hann)."""
+    rc = _lib.load().wfl_stft_mag(_ptr(y), y.numel(), n_fft, hop, power, _ptr(out), _stream())
+    _lib.check(rc, "wfl_stft_mag")
+    _count(1)
+
+
+def spectral_flux(S, flux):
+    rc = _lib.load().wfl_spectral_flux(_ptr(S), S.shape[0], S.shape[1], _ptr(flux), _stream())
+    _lib.check(rc, "wfl_spectral_flux")
+    _count(1)
+
+
+def mfcc_delta_mag(P, mel_fb, mel_span, dct, delta_mag):
+    frames, bins = P.shape
+    n_mels, n_mfcc = mel_fb.shape[0], dct.shape[0]
+    db = torch.empty(frames, n_mels, device=P.device)
+    mf = torch.empty(frames, n_mfcc, device=P.device)
+    mx = torch.empty(1, dtype=torch.int32, device=P.device)
+    rc = _lib.load().wfl_mfcc_delta_mag(_ptr(P), frames, bins, _ptr(mel_fb), _ptr(mel_span), n_mels, _ptr(dct), n_mfcc,
+                                        _ptr(db), _ptr(mf), _ptr(mx), _ptr(delta_mag), _stream())
+    _lib.check(rc, "wfl_mfcc_delta_mag")
+    _count(3)
+    return mf
+
+
 def logmel_scratch(B, n_mels, device):
     """Scratch buffers of wfl_whisper_logmel: (planes f16, dft fp32 [B,3000,448], logspec fp32, clip max + filter spans)."""
     from .frontend import PLANE_SAMPLES
