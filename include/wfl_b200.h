@@ -277,8 +277,10 @@ int wfl_mfcc_delta_mag(const float* P, int32_t frames, int32_t bins, const float
  * fold) and owns them plus a workspace arena (sized for config.max_batch at finalize, grown on demand outside stream
  * capture).  The caller owns every input / output buffer; all work is enqueued on the caller's stream.  Repeated
  * wfl_forward calls on the same buffers replay a CUDA graph captured on the second call.  One handle per device,
- * not re-entrant.  Scope: encoder_type whisper (WavLM and the mel front-end stay with the Python engine:
- * wfl_finalize returns WFL_ERR_UNSUPPORTED). */
+ * not re-entrant.  Scope: encoder_type whisper and wavlm (the mel front-end stays with the Python engine:
+ * wfl_finalize returns WFL_ERR_UNSUPPORTED).  WavLM's frame count follows the clip length (WFL_QUERY_FRAMES), its
+ * arena grows with (B, N), and the first pass at a new clip length must not run inside a stream capture (it builds
+ * the relative-position bias table for that length). */
 #define WFL_ENCODER_WHISPER 0
 #define WFL_ENCODER_WAVLM 1
 #define WFL_ENCODER_NONE 2
@@ -291,6 +293,8 @@ typedef struct wfl_config {
   int32_t n_labels, n_languages, lang_emb_dim;                                    /* REF/model.py:97-98,135         */
   int32_t precision_high;                /* 1 = [hi | lo] attention value / output weights   */
   int32_t max_batch;                     /* workspace sized for this many clips at finalize (0 = on first forward) */
+  int32_t wavlm_layer_norm;              /* WavLM only: 1 = feat_extract_norm "layer" + stable layer norm (wavlm-large),
+                                            0 = GroupNorm conv0 + post-LN layers (wavlm-base, -base-plus)           */
 } wfl_config;
 typedef struct wfl_handle wfl_handle;
 
@@ -309,6 +313,10 @@ enum wfl_query_what {
   WFL_QUERY_GRAPHS = 3           /* captured CUDA graphs currently cached                                           */
 };
 int wfl_query(wfl_handle* handle, int32_t what, int64_t arg, int64_t* value);
+/* Diagnostic: the device copy of one packed weight by its kernel-side name ("enc0.qkv.w", "lang.w3", "cls.w" ...;
+ * DESIGN.md section 3 lists them) so a binding can check its packer against this one; "ws.<name>" returns a
+ * workspace buffer's address with bytes = 0.  The handle keeps ownership. */
+int wfl_packed_buffer(wfl_handle* handle, const char* name, const void** dev_ptr, int64_t* bytes);
 /* REF/model.py:148-194: wave fp32 [B][wave_stride] (N valid samples per clip, 16 kHz), lang ids int64 [B] or NULL
  * (NULL skips lang_proj, REF/model.py:176) -> logits fp32 [B][T][logits_stride] (first n_labels columns valid),
  * offsets fp32 [B][T][2]. */

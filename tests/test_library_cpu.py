@@ -43,17 +43,18 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "wfl_b200.h"\n'
-        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %d %d %zu %zu %zu\\n", sizeof(wfl_gemm_desc), offsetof(wfl_gemm_desc, w), '
+        'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %d %d %zu %zu %zu %zu\\n", sizeof(wfl_gemm_desc), offsetof(wfl_gemm_desc, w), '
         'offsetof(wfl_gemm_desc, bias), offsetof(wfl_gemm_desc, out), offsetof(wfl_gemm_desc, tile_n), '
         'offsetof(wfl_gemm_desc, out_col_group_stride), sizeof(wfl_segment), (int)WFL_MAX_SLABS, (int)WFL_WAVLM_STATS_DOUBLES, '
-        'sizeof(wfl_config), offsetof(wfl_config, n_labels), offsetof(wfl_config, max_batch)); return 0; }\n')
+        'sizeof(wfl_config), offsetof(wfl_config, n_labels), offsetof(wfl_config, max_batch), offsetof(wfl_config, wavlm_layer_norm)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     G = _lib.GemmDesc
     want = [ctypes.sizeof(G), G.w.offset, G.bias.offset, G.out.offset, G.tile_n.offset, G.out_col_group_stride.offset,
             ctypes.sizeof(_lib.Segment), _lib.WFL_MAX_SLABS, ops.WAVLM_STATS_DOUBLES,
-            ctypes.sizeof(_lib.Config), _lib.Config.n_labels.offset, _lib.Config.max_batch.offset]
+            ctypes.sizeof(_lib.Config), _lib.Config.n_labels.offset, _lib.Config.max_batch.offset,
+            _lib.Config.wavlm_layer_norm.offset]
     assert got == want, (got, want)
 
 

@@ -44,7 +44,7 @@ class Config(_C.Structure):
     _fields_ = [(n, _C.c_int32) for n in (
         "encoder_type", "d", "layers", "heads", "ffn", "mels", "enable_bilstm", "bilstm_layers", "n_conformer",
         "conformer_heads", "conformer_ff_expansion", "conformer_kernel", "enable_dilated", "dilated_depth",
-        "dilated_kernel", "n_labels", "n_languages", "lang_emb_dim", "precision_high", "max_batch")]
+        "dilated_kernel", "n_labels", "n_languages", "lang_emb_dim", "precision_high", "max_batch", "wavlm_layer_norm")]
 
 
 class Segment(_C.Structure):
@@ -85,6 +85,7 @@ SIGNATURES = {
     "wfl_finalize": [_P],
     "wfl_set_labels": [_P, _C.POINTER(_C.c_char_p), _I32],
     "wfl_query": [_P, _I32, _I64, _C.POINTER(_I64)],
+    "wfl_packed_buffer": [_P, _C.c_char_p, _C.POINTER(_P), _C.POINTER(_I64)],
     "wfl_forward": [_P, _P, _I64, _P, _I32, _I32, _P, _P, _P],
     "wfl_postprocess": [_P, _P, _P, _P, _I32, _I32, _F, _I32, _I32, _P, _P, _P],
 }

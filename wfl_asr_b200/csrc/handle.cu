@@ -184,6 +184,7 @@ __global__ void fill_index_kernel(const int32_t* __restrict__ frames, int T, int
 struct Handle {
   wfl_config cfg;
   std::map<std::string, Mat> sd;
+  Mat sd_rel_emb;  // WavLM rel_attn_embed [320, H], kept on the host for the per-length bias tables
   std::map<std::string, DevBuf> W;
   bool finalized = false;
   int device = 0;
@@ -197,6 +198,9 @@ struct Handle {
   // labels (post-processing)
   DevBuf label_kind, label_ph;
   int n_label_entries = 0, o_id = -1;
+  // WavLM: bucketed relative-position bias tables [H][2T-1], one per sequence length seen
+  std::map<int, DevBuf> rel_tables;
+  int64_t arena_samples = 0, arena_frames = 0;
   // graphs
   std::vector<GraphEntry> graphs;
   bool use_graphs = true;
@@ -204,6 +208,7 @@ struct Handle {
   ~Handle() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
     for (auto& kv : W) cudaFree(kv.second.p);
+    for (auto& kv : rel_tables) cudaFree(kv.second.p);
     if (label_kind.p) cudaFree(label_kind.p);
     if (label_ph.p) cudaFree(label_ph.p);
     if (arena) cudaFree(arena);
@@ -364,6 +369,145 @@ int pack_whisper(Handle* h) {
   }
   TRY(pack_ln(h, "enc.ln", "encoder.layer_norm"));
   return pack_frontend(h);
+}
+
+constexpr int kWavlmKernels[7] = {10, 3, 3, 3, 3, 2, 2};
+constexpr int kWavlmStrides[7] = {5, 2, 2, 2, 2, 2, 2};
+void wavlm_lengths(int64_t n, int64_t (&out)[7]) {
+  for (int i = 0; i < 7; ++i) {
+    n = n < kWavlmKernels[i] ? 0 : (n - kWavlmKernels[i]) / kWavlmStrides[i] + 1;  // floor, never negative
+    out[i] = n;
+  }
+}
+
+// engine._pack_wavlm (TF/models/wavlm/modeling_wavlm.py weights -> kernel layouts)
+int pack_wavlm(Handle* h) {
+  const wfl_config& c = h->cfg;
+  const int d = h->d;
+  const bool large = c.wavlm_layer_norm != 0;
+  const std::string fe = "encoder.feature_extractor.conv_layers.";
+  {
+    NEED(w0, fe + "0.conv.weight");  // [512, 1, 10]
+    TRY(put_f32(h, "wl.c0.w", *w0));
+    TRY(pack_ln(h, "wl.c0.ln", fe + "0.layer_norm"));
+  }
+  for (int i = 1; i < 7; ++i) {
+    NEED(w, fe + std::to_string(i) + ".conv.weight");
+    TRY(put_f16(h, "wl.c" + std::to_string(i) + ".w", conv_taps(*w, 512)));
+    if (large) TRY(pack_ln(h, "wl.c" + std::to_string(i) + ".ln", fe + std::to_string(i) + ".layer_norm"));
+  }
+  TRY(pack_ln(h, "wl.fp.ln", "encoder.feature_projection.layer_norm"));
+  {
+    NEED(w, "encoder.feature_projection.projection.weight");
+    NEED(b, "encoder.feature_projection.projection.bias");
+    TRY(pack_linear(h, "wl.fp", *w, b));
+  }
+  {  // positional conv: weight_norm(dim = 2) folded, 16 groups as one grouped contraction with 64-wide K slabs
+    const std::string pc = "encoder.encoder.pos_conv_embed.conv.";
+    NEED(g, pc + "parametrizations.weight.original0");  // [1, 1, K]
+    NEED(v, pc + "parametrizations.weight.original1");  // [d, d / 16, K]
+    NEED(b, pc + "bias");
+    const int K = 128, G = 16, cg = d / G;
+    std::vector<double> norm(K, 0.0);
+    for (int o = 0; o < d; ++o)
+      for (int i = 0; i < cg; ++i)
+        for (int k = 0; k < K; ++k) {
+          const double x = v->v[(static_cast<size_t>(o) * cg + i) * K + k];
+          norm[k] += x * x;
+        }
+    Mat wp;
+    wp.shape = {d, static_cast<int64_t>(K) * 64};
+    wp.v.assign(static_cast<size_t>(d) * K * 64, 0.f);
+    for (int k = 0; k < K; ++k) {
+      const double scale = static_cast<double>(g->v[k]) / sqrt(norm[k]);
+      for (int o = 0; o < d; ++o)
+        for (int i = 0; i < cg; ++i)
+          wp.v[(static_cast<size_t>(o) * K + k) * 64 + i] = static_cast<float>(static_cast<double>(v->v[(static_cast<size_t>(o) * cg + i) * K + k]) * scale);
+    }
+    TRY(put_f16(h, "wl.pos.w", wp));
+    TRY(put_f32(h, "wl.pos.b", *b));
+  }
+  TRY(pack_ln(h, "wl.enc.ln", "encoder.encoder.layer_norm"));
+  for (int i = 0; i < c.layers; ++i) {
+    const std::string p = "encoder.encoder.layers." + std::to_string(i) + ".", pa = p + "attention.", q = "wl" + std::to_string(i) + ".";
+    NEED(wq, pa + "q_proj.weight");
+    NEED(wk, pa + "k_proj.weight");
+    NEED(wv, pa + "v_proj.weight");
+    NEED(bq, pa + "q_proj.bias");
+    NEED(bk, pa + "k_proj.bias");
+    NEED(bv, pa + "v_proj.bias");
+    NEED(wo, pa + "out_proj.weight");
+    NEED(bo, pa + "out_proj.bias");
+    Mat bias;
+    bias.shape = {3 * d};
+    bias.v.resize(static_cast<size_t>(3) * d);
+    memcpy(bias.v.data(), bq->v.data(), sizeof(float) * d);
+    memcpy(bias.v.data() + d, bk->v.data(), sizeof(float) * d);
+    memcpy(bias.v.data() + 2 * d, bv->v.data(), sizeof(float) * d);
+    TRY(pack_linear(h, q + "qkv", cat_rows({wq, wk, wv}), &bias));
+    TRY(pack_linear(h, q + "out", *wo, bo));
+    if (c.precision_high) {
+      TRY(put_u16(h, q + "v.w2", split_hi_lo(pad_k(*wv, pad64(d)), 0, "hl")));
+      TRY(put_u16(h, q + "out.w2", split_hi_lo(*wo, 0, "hl")));
+    }
+    NEED(gw, pa + "gru_rel_pos_linear.weight");
+    NEED(gb, pa + "gru_rel_pos_linear.bias");
+    NEED(gc, pa + "gru_rel_pos_const");
+    TRY(put_f32(h, q + "gate.w", *gw));
+    TRY(put_f32(h, q + "gate.b", *gb));
+    TRY(put_f32(h, q + "gate.c", *gc));
+    TRY(pack_ln(h, q + "ln1", p + "layer_norm"));
+    TRY(pack_ln(h, q + "ln2", p + "final_layer_norm"));
+    NEED(f1, p + "feed_forward.intermediate_dense.weight");
+    NEED(f1b, p + "feed_forward.intermediate_dense.bias");
+    NEED(f2, p + "feed_forward.output_dense.weight");
+    NEED(f2b, p + "feed_forward.output_dense.bias");
+    TRY(pack_linear(h, q + "fc1", *f1, f1b));
+    TRY(pack_linear(h, q + "fc2", *f2, f2b));
+  }
+  NEED(rel, "encoder.encoder.layers.0.attention.rel_attn_embed.weight");  // [320, H]
+  h->sd_rel_emb = *rel;
+  return WFL_OK;
+}
+
+// engine._rel_bias_table: [H][2T-1] bucketed relative-position embedding over rel = key - query
+// (TF/models/wavlm/modeling_wavlm.py:243-271), built once per sequence length
+int rel_bias_table(Handle* h, int T, const float** out) {
+  auto it = h->rel_tables.find(T);
+  if (it != h->rel_tables.end()) {
+    *out = static_cast<const float*>(it->second.p);
+    return WFL_OK;
+  }
+  const int H = h->cfg.heads, nb = 320 / 2, max_exact = nb / 2;
+  const float log_ratio = static_cast<float>(log(800.0 / max_exact));
+  std::vector<float> tab(static_cast<size_t>(H) * (2 * T - 1));
+  for (int r = -(T - 1); r <= T - 1; ++r) {
+    int bucket = r > 0 ? nb : 0;
+    const int a = r < 0 ? -r : r;
+    if (a < max_exact) {
+      bucket += a;
+    } else {
+      const float lf = logf(static_cast<float>(a) / static_cast<float>(max_exact)) / log_ratio * static_cast<float>(nb - max_exact);
+      int large = max_exact + static_cast<int>(lf);
+      if (large > nb - 1) large = nb - 1;
+      bucket += large;
+    }
+    for (int hh = 0; hh < H; ++hh) tab[static_cast<size_t>(hh) * (2 * T - 1) + (r + T - 1)] = h->sd_rel_emb.v[static_cast<size_t>(bucket) * H + hh];
+  }
+  DevBuf b;
+  b.bytes = tab.size() * 4;
+  WFL_CUDA(cudaMalloc(&b.p, b.bytes));
+  WFL_CUDA(cudaMemcpy(b.p, tab.data(), b.bytes, cudaMemcpyHostToDevice));
+  if (h->rel_tables.size() >= 64) {  // bounded: drop an arbitrary old table (graphs that used it are dropped with it)
+    for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    WFL_CUDA(cudaDeviceSynchronize());
+    cudaFree(h->rel_tables.begin()->second.p);
+    h->rel_tables.erase(h->rel_tables.begin());
+  }
+  h->rel_tables[T] = b;
+  *out = static_cast<const float*>(b.p);
+  return WFL_OK;
 }
 
 int pack_bilstm(Handle* h) {
@@ -549,11 +693,20 @@ int pack_head(Handle* h) {
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
-int ensure_workspace(Handle* h, int B) {
-  if (B <= h->arena_batch) return WFL_OK;
+// The arena holds every activation of one pass.  Whisper pads each clip to 30 s, so its size depends on the batch
+// only; WavLM's frame count follows the clip length, so its arena grows with (B, N) -- monotonically in both.
+int ensure_workspace(Handle* h, int B, int64_t N) {
   const wfl_config& c = h->cfg;
-  const int64_t T = 1500, M = static_cast<int64_t>(B) * T, d = h->d;
+  const bool wavlm = c.encoder_type == WFL_ENCODER_WAVLM;
+  if (B <= h->arena_batch && (!wavlm || N <= h->arena_samples)) return WFL_OK;
+  if (B < h->arena_batch) B = h->arena_batch;
+  if (wavlm && N < h->arena_samples) N = h->arena_samples;
+  int64_t Ts[7] = {0, 0, 0, 0, 0, 0, 1500};
+  if (wavlm) wavlm_lengths(N, Ts);
+  const int64_t T = Ts[6], M = static_cast<int64_t>(B) * T, d = h->d;
   const int64_t F = h->ffn_max;
+  const bool large = c.wavlm_layer_norm != 0;
+  const int64_t wh = wavlm ? 0 : 1, wl = wavlm ? 1 : 0;  // which encoder's private buffers exist
   struct Item {
     const char* name;
     int64_t bytes;
@@ -566,9 +719,13 @@ int ensure_workspace(Handle* h, int B) {
   std::vector<Item> items = {
       {"x", M * d * 4},        {"h", M * d * 2},          {"qkv", M * qkv_w * 2},      {"ctx", M * ctx_w * 2},
       {"u", M * F * 2},        {"g", M * h->dk * 2},      {"c", M * d * 2},            {"hl", M * 2 * d * 2},
-      {"y", M * d * 4},        {"feats", B * 3000LL * 128 * 2}, {"h1", B * 3000LL * d * 2},
-      {"planes", (2 * plane * B + 4096) * 2}, {"dft", B * 3000LL * 448 * 4}, {"logspec", B * 3000LL * c.mels * 4},
-      {"smax", (B + 258) * 4LL}, {"langb", static_cast<int64_t>(B) * d * 4},
+      {"y", M * d * 4},        {"feats", wh * B * 3000LL * 128 * 2}, {"h1", wh * B * 3000LL * d * 2},
+      {"planes", wh * (2 * plane * B + 4096) * 2}, {"dft", wh * B * 3000LL * 448 * 4}, {"logspec", wh * B * 3000LL * c.mels * 4},
+      {"smax", wh * (B + 258) * 4LL}, {"langb", static_cast<int64_t>(B) * d * 4},
+      // WavLM conv stack: activations ping-pong (+ spill rows of the paired-row view), fp32 pre-norm rows, gate
+      {"cA", wl * (B * Ts[0] + 2) * 512 * 2}, {"cB", wl * (B * Ts[1] + 2) * 512 * 2},
+      {"cf", wl * B * (large ? Ts[1] : Ts[6]) * 512 * 4}, {"h512", wl * M * 512 * 2},
+      {"wstats", wl * WFL_WAVLM_STATS_DOUBLES * 8LL * B}, {"gate", wl * static_cast<int64_t>(B) * c.heads * T * 4},
       {"gx", c.enable_bilstm ? M * 8 * Hp * 4 : 0}, {"ylstm", (c.enable_bilstm && Hp != h->lstm_h) ? M * 2 * Hp * 4 : 0},
       // post-processing
       {"ids", M * 4}, {"ids2", M * 4}, {"segs", M * 24}, {"lengths", B * 4LL}, {"fcb", (B + 1) * 4LL}, {"nseg", B * 4LL},
@@ -587,6 +744,8 @@ int ensure_workspace(Handle* h, int B) {
   WFL_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->arena), total));
   h->arena_bytes = total;
   h->arena_batch = B;
+  h->arena_samples = wavlm ? N : 0;
+  h->arena_frames = T;
   size_t off = 0;
   h->ws.clear();
   for (const Item& it : items) {
@@ -631,6 +790,10 @@ int linear(cudaStream_t s, const void* a, int64_t a_stride, int64_t M, int64_t K
   return wfl_gemm(&g.d, s);
 }
 
+// head_dim ** -0.5 evaluated in double and rounded once, like the Python engine's `hd ** -0.5` (384 and 640 are not
+// powers of four: a float sqrt + divide lands one ulp away and moves context vectors by an f16 ulp)
+float attn_scale(int hd) { return static_cast<float>(pow(static_cast<double>(hd), -0.5)); }
+
 const void* Wp(Handle* h, const std::string& name) {
   auto it = h->W.find(name);
   return it == h->W.end() ? nullptr : it->second.p;
@@ -662,7 +825,7 @@ int whisper_attention_block(Handle* h, cudaStream_t s, const std::string& q, int
   } else {
     TRY(linear(s, hbuf, d, M, d, w, 3 * d, d, b, qkv, 3 * d, WFL_ACT_NONE, WFL_OUT_STORE_F16));
   }
-  TRY(wfl_attention(qkv, 3 * d, static_cast<int64_t>(T) * 3 * d, 0, d, 2 * d, B, T, H, hd, 1.0f / sqrtf(static_cast<float>(hd)),
+  TRY(wfl_attention(qkv, 3 * d, static_cast<int64_t>(T) * 3 * d, 0, d, 2 * d, B, T, H, hd, attn_scale(hd),
                     nullptr, nullptr, ctx, d, static_cast<int64_t>(T) * d, s));
   if (h->cfg.precision_high)
     return linear(s, ctx, d, M, d, Wp(h, q + "out.w2"), d, d, Wf(h, q + "out.b"), x, d, WFL_ACT_NONE, WFL_OUT_ADD_F32, 1.0f, 0, 2);
@@ -742,6 +905,140 @@ int whisper_encoder(Handle* h, cudaStream_t s, const float* wave, int64_t wave_s
   return WFL_OK;
 }
 
+// engine._wavlm_encoder (REF/model.py:159-161 -> TF/models/wavlm/modeling_wavlm.py:1039-1095, attention_mask = None):
+// wavlm-base(-plus) = GroupNorm conv0 + post-LN layers; wavlm-large = LayerNorm convs + pre-LN layers.
+// Leaves x (fp32 [B, T, d]) = the hidden states BEFORE the encoder's final LayerNorm (large) / the final states (base).
+int wavlm_encoder(Handle* h, cudaStream_t s, const float* wave, int64_t wave_stride, int B, int N, int* T_out) {
+  const wfl_config& c = h->cfg;
+  const int d = h->d, H = c.heads, hd = d / H;
+  const bool large = c.wavlm_layer_norm != 0;
+  int64_t Ts[7];
+  wavlm_lengths(N, Ts);
+  const int T = static_cast<int>(Ts[6]);
+  const int64_t M = static_cast<int64_t>(B) * T, F = h->ffn_max;
+  *T_out = T;
+  __half* cA = WS<__half>(h, "cA");
+  __half* cB = WS<__half>(h, "cB");
+  float* cf = WS<float>(h, "cf");
+  __half* h512 = WS<__half>(h, "h512");
+  TRY(wfl_wavlm_conv0(wave, wave_stride, N, B, Wf(h, "wl.c0.w"), Wf(h, "wl.c0.ln.g"), Wf(h, "wl.c0.ln.b"), large ? 1 : 0, cA,
+                      Ts[0] * 512, WS<double>(h, "wstats"), s));
+  __half *src = cA, *dst = cB;
+  for (int i = 1; i < 7; ++i) {
+    const int k = kWavlmKernels[i];
+    const int64_t t_in = Ts[i - 1], t_out = Ts[i];
+    const bool last = i == 6;
+    const std::string name = "wl.c" + std::to_string(i);
+    // stride-2 conv over the paired-row view [ceil(t_in / 2), 1024]: taps 0, 1 = the pair, tap 2 = the next pair's first
+    Gemm g;
+    g.d.a = src;
+    g.d.a_rows = (t_in + 1) / 2;
+    g.d.a_cols = 1024;
+    g.d.a_row_stride = 1024;
+    g.d.a_batch_stride = t_in * 512;
+    g.d.batches = B;
+    g.d.w = Wp(h, name + ".w");
+    g.d.n = 512;
+    g.d.slab_k = 512;
+    g.d.num_slabs = k;
+    g.d.slab_a_col[1] = 512;
+    if (k == 3) g.d.slab_row_shift[2] = 1;
+    g.d.m_rows = t_out;
+    g.d.out_row_stride = 512;
+    g.d.out_batch_stride = t_out * 512;
+    if (large) {
+      g.d.out = cf;
+      g.d.out_mode = WFL_OUT_STORE_F32;
+      TRY(wfl_gemm(&g.d, s));
+      const float *g1 = Wf(h, name + ".ln.g"), *b1 = Wf(h, name + ".ln.b");
+      if (last)  // LayerNorm + GELU, then the feature-projection LayerNorm, in one pass
+        TRY(wfl_layernorm(cf, B * t_out, 512, g1, b1, Wf(h, "wl.fp.ln.g"), Wf(h, "wl.fp.ln.b"), 1e-5f, nullptr, h512, WFL_ACT_GELU, s));
+      else
+        TRY(wfl_layernorm(cf, B * t_out, 512, g1, b1, nullptr, nullptr, 1e-5f, nullptr, dst, WFL_ACT_GELU, s));
+    } else if (last) {
+      g.d.out = cf;
+      g.d.act = WFL_ACT_GELU;
+      g.d.out_mode = WFL_OUT_STORE_F32;
+      TRY(wfl_gemm(&g.d, s));
+      TRY(wfl_layernorm(cf, M, 512, Wf(h, "wl.fp.ln.g"), Wf(h, "wl.fp.ln.b"), nullptr, nullptr, 1e-5f, nullptr, h512, WFL_ACT_NONE, s));
+    } else {
+      g.d.out = dst;
+      g.d.act = WFL_ACT_GELU;
+      g.d.out_mode = WFL_OUT_STORE_F16;
+      TRY(wfl_gemm(&g.d, s));
+    }
+    __half* t = src;
+    src = dst;
+    dst = t;
+  }
+  float* x = WS<float>(h, "x");
+  __half* hbuf = WS<__half>(h, "h");
+  __half* hl = WS<__half>(h, "hl");
+  __half* qkv = WS<__half>(h, "qkv");
+  __half* ctx = WS<__half>(h, "ctx");
+  __half* u = WS<__half>(h, "u");
+  float* gate = WS<float>(h, "gate");
+  // feature projection -> fp32 hidden states
+  TRY(linear(s, h512, 512, M, 512, Wp(h, "wl.fp.w"), d, 512, Wf(h, "wl.fp.b"), x, d, WFL_ACT_NONE, WFL_OUT_STORE_F32));
+  // positional conv (k128, pad 64, 16 groups, weight norm folded) + GELU, added to x: ONE grouped implicit GEMM
+  TRY(wfl_split_f16(x, M, d, hl, s));
+  {
+    const int G = 16, K = 128, cg = d / G;
+    Gemm g;
+    g.d.a = hl;
+    g.d.a_rows = T;
+    g.d.a_cols = d;
+    g.d.a_row_stride = 2 * d;
+    g.d.a_batch_stride = static_cast<int64_t>(T) * 2 * d;
+    g.d.batches = B;
+    g.d.w = Wp(h, "wl.pos.w");
+    g.d.n = cg;
+    g.d.slab_k = 64;
+    g.d.num_slabs = K;
+    for (int j = 0; j < K; ++j) g.d.slab_row_shift[j] = j - K / 2;
+    g.d.bias = Wf(h, "wl.pos.b");
+    g.d.act = WFL_ACT_GELU;
+    g.d.out_mode = WFL_OUT_ADD_F32;
+    g.d.out = x;
+    g.d.m_rows = T;
+    g.d.out_row_stride = d;
+    g.d.out_batch_stride = static_cast<int64_t>(T) * d;
+    g.d.tile_n = 128;
+    g.d.groups = G;
+    g.d.a_col_group_stride = cg;
+    g.d.out_col_group_stride = cg;
+    TRY(wfl_gemm(&g.d, s));
+  }
+  const float* tab = nullptr;
+  TRY(rel_bias_table(h, T, &tab));
+  if (!large) TRY(ln(h, s, x, M, "wl.enc.ln", x, hbuf));
+  for (int i = 0; i < c.layers; ++i) {
+    const std::string q = "wl" + std::to_string(i) + ".";
+    if (large) TRY(ln(h, s, x, M, q + "ln1", nullptr, hbuf));
+    const __half* w = static_cast<const __half*>(Wp(h, q + "qkv.w"));
+    const float* b = Wf(h, q + "qkv.b");
+    if (c.precision_high) {
+      TRY(linear(s, hbuf, d, M, d, w, 2 * d, d, b, qkv, 3 * d, WFL_ACT_NONE, WFL_OUT_STORE_F16));
+      TRY(linear(s, hbuf, d, M, d, Wp(h, q + "v.w2"), d, d, b + 2 * d, qkv + 2 * d, 3 * d, WFL_ACT_NONE, WFL_OUT_STORE_F16, 1.0f, 0, 2));
+    } else {
+      TRY(linear(s, hbuf, d, M, d, w, 3 * d, d, b, qkv, 3 * d, WFL_ACT_NONE, WFL_OUT_STORE_F16));
+    }
+    TRY(wfl_wavlm_gate(hbuf, d, B, T, H, hd, Wf(h, q + "gate.w"), Wf(h, q + "gate.b"), Wf(h, q + "gate.c"), gate, s));
+    TRY(wfl_attention(qkv, 3 * d, static_cast<int64_t>(T) * 3 * d, 0, d, 2 * d, B, T, H, hd, attn_scale(hd),
+                      tab, gate, ctx, d, static_cast<int64_t>(T) * d, s));
+    if (c.precision_high)
+      TRY(linear(s, ctx, d, M, d, Wp(h, q + "out.w2"), d, d, Wf(h, q + "out.b"), x, d, WFL_ACT_NONE, WFL_OUT_ADD_F32, 1.0f, 0, 2));
+    else
+      TRY(linear(s, ctx, d, M, d, Wp(h, q + "out.w"), d, d, Wf(h, q + "out.b"), x, d, WFL_ACT_NONE, WFL_OUT_ADD_F32));
+    if (large) TRY(ln(h, s, x, M, q + "ln2", nullptr, hbuf));
+    else TRY(ln(h, s, x, M, q + "ln1", x, hbuf));
+    TRY(linear(s, hbuf, d, M, d, Wp(h, q + "fc1.w"), c.ffn, d, Wf(h, q + "fc1.b"), u, F, WFL_ACT_GELU, WFL_OUT_STORE_F16));
+    TRY(linear(s, u, F, M, c.ffn, Wp(h, q + "fc2.w"), d, pad64(c.ffn), Wf(h, q + "fc2.b"), x, d, WFL_ACT_NONE, WFL_OUT_ADD_F32));
+    if (!large) TRY(ln(h, s, x, M, q + "ln2", x, hbuf));
+  }
+  return WFL_OK;
+}
+
 // engine._conformer (REF/model.py:40-52) on the fp32 residual stream x
 int conformer(Handle* h, cudaStream_t s, int i, int B, int T) {
   const wfl_config& c = h->cfg;
@@ -777,7 +1074,7 @@ int conformer(Handle* h, cudaStream_t s, int i, int B, int T) {
     TRY(linear(s, hl, 2 * d, M, d, w_in, 3 * aw, dk, b_in, qkv, 3 * aw, WFL_ACT_NONE, WFL_OUT_STORE_F16));
   }
   TRY(wfl_attention(qkv, 3 * aw, static_cast<int64_t>(T) * 3 * aw, 0, aw, 2 * aw, B, T, H, h->conf_hdp,
-                    1.0f / sqrtf(static_cast<float>(d / H)), nullptr, nullptr, ctx, aw, static_cast<int64_t>(T) * aw, s));
+                    attn_scale(d / H), nullptr, nullptr, ctx, aw, static_cast<int64_t>(T) * aw, s));
   if (c.precision_high)
     TRY(linear(s, ctx, aw, M, aw, Wp(h, q + "attn.out.w2"), d, aw, Wf(h, q + "attn.out.b"), x, d, WFL_ACT_NONE, WFL_OUT_ADD_F32, 1.0f, 0, 2));
   else
@@ -848,13 +1145,13 @@ int split_gemm(cudaStream_t s, const void* hl, int d, int dk, int B, int T, cons
 }
 
 // engine._head: everything after the encoder (REF/model.py:166-194), lang_id may be null
-int head(Handle* h, cudaStream_t s, const int64_t* lang, int B, int T, float* logits, float* offsets) {
+int head(Handle* h, cudaStream_t s, const int64_t* lang, int B, int T, const char* final_ln, float* logits, float* offsets) {
   const wfl_config& c = h->cfg;
   const int d = h->d, dk = h->dk;
   const int64_t M = static_cast<int64_t>(B) * T;
   float* x = WS<float>(h, "x");
   __half* hl = WS<__half>(h, "hl");
-  TRY(ln(h, s, x, M, "enc.ln", x, nullptr));  // the encoder's last_hidden_state, fp32
+  if (final_ln != nullptr) TRY(ln(h, s, x, M, final_ln, x, nullptr));  // the encoder's last_hidden_state, fp32
   if (lang != nullptr || c.enable_bilstm) TRY(wfl_split_f16(x, M, d, hl, s));
   if (lang != nullptr) {
     float* lb = WS<float>(h, "langb");
@@ -955,8 +1252,14 @@ int head(Handle* h, cudaStream_t s, const int64_t* lang, int B, int T, float* lo
 
 int run_forward(Handle* h, cudaStream_t s, const float* wave, int64_t wave_stride, const int64_t* lang, int B, int N,
                 float* logits, float* offsets) {
+  if (h->cfg.encoder_type == WFL_ENCODER_WAVLM) {
+    int T = 0;
+    TRY(wavlm_encoder(h, s, wave, wave_stride, B, N, &T));
+    // stable-layer-norm models (wavlm-large) normalise once more after the last layer; wavlm-base(-plus) does not
+    return head(h, s, lang, B, T, h->cfg.wavlm_layer_norm ? "wl.enc.ln" : nullptr, logits, offsets);
+  }
   TRY(whisper_encoder(h, s, wave, wave_stride, B, N));
-  return head(h, s, lang, B, 1500, logits, offsets);
+  return head(h, s, lang, B, 1500, "enc.ln", logits, offsets);
 }
 
 }  // namespace
@@ -966,6 +1269,10 @@ using namespace wfl;
 
 extern "C" int wfl_create(const wfl_config* config, wfl_handle** out) {
   WFL_CHECK_ARG(config && out, "wfl_create: null pointer");
+  if (config->encoder_type != WFL_ENCODER_WHISPER && config->encoder_type != WFL_ENCODER_WAVLM) {
+    set_error("wfl_create: the handle API serves encoder_type whisper and wavlm; the mel front-end runs through the Python engine");
+    return WFL_ERR_UNSUPPORTED;
+  }
   WFL_CHECK_ARG(config->d > 0 && config->d % 64 == 0, "wfl_create: hidden size %d must be a positive multiple of 64", config->d);
   WFL_CHECK_ARG(config->n_labels > 0 && config->n_languages > 0 && config->lang_emb_dim > 0, "wfl_create: bad label / language counts");
   WFL_CHECK_ARG(config->conformer_heads > 0 && config->d % config->conformer_heads == 0,
@@ -1003,8 +1310,8 @@ extern "C" int wfl_finalize(wfl_handle* handle) {
   Handle* h = reinterpret_cast<Handle*>(handle);
   WFL_CHECK_ARG(h, "wfl_finalize: null handle");
   const wfl_config& c = h->cfg;
-  if (c.encoder_type != WFL_ENCODER_WHISPER) {
-    set_error("wfl_finalize: the handle API serves encoder_type whisper; WavLM / mel front-ends run through the Python engine");
+  if (c.encoder_type != WFL_ENCODER_WHISPER && c.encoder_type != WFL_ENCODER_WAVLM) {
+    set_error("wfl_finalize: the handle API serves encoder_type whisper and wavlm; the mel front-end runs through the Python engine");
     return WFL_ERR_UNSUPPORTED;
   }
   const int hd = c.d / c.conformer_heads;
@@ -1026,12 +1333,18 @@ extern "C" int wfl_finalize(wfl_handle* handle) {
   h->ffn_max = c.ffn;
   if (c.conformer_ff_expansion * c.d > h->ffn_max) h->ffn_max = c.conformer_ff_expansion * c.d;
   if (2 * c.d > h->ffn_max) h->ffn_max = 2 * c.d;
-  WFL_CHECK_ARG(c.d % c.heads == 0 && c.d / c.heads == 64, "wfl_finalize: Whisper encoders have head dim 64 (d %d, heads %d)", c.d, c.heads);
-  TRY(pack_whisper(h));
+  WFL_CHECK_ARG(c.heads > 0 && c.d % c.heads == 0 && c.d / c.heads == 64, "wfl_finalize: Whisper / WavLM encoders have head dim 64 (d %d, heads %d)", c.d, c.heads);
+  if (c.encoder_type == WFL_ENCODER_WAVLM) {
+    WFL_CHECK_ARG(c.d % 16 == 0 && c.d / 16 <= 64, "wfl_finalize: WavLM positional conv groups of %d channels exceed 64", c.d / 16);
+    TRY(pack_wavlm(h));
+  } else {
+    TRY(pack_whisper(h));
+  }
   TRY(pack_head(h));
   h->sd.clear();  // the packed device copies are what the handle owns from here on
   h->finalized = true;
-  if (c.max_batch > 0) TRY(ensure_workspace(h, c.max_batch));
+  // WavLM's arena follows the clip length: pre-size it for 10 s clips (it grows on a longer first batch)
+  if (c.max_batch > 0) TRY(ensure_workspace(h, c.max_batch, 160000));
   return WFL_OK;
 }
 
@@ -1040,11 +1353,48 @@ extern "C" int wfl_query(wfl_handle* handle, int32_t what, int64_t arg, int64_t*
   WFL_CHECK_ARG(h && value, "wfl_query: null pointer");
   switch (what) {
     case WFL_QUERY_LOGITS_STRIDE: *value = h->Lp; return WFL_OK;
-    case WFL_QUERY_FRAMES: *value = 1500; (void)arg; return WFL_OK;  // Whisper pads / truncates every clip to 30 s
+    case WFL_QUERY_FRAMES:
+      if (h->cfg.encoder_type == WFL_ENCODER_WAVLM) {  // seven strided convs (TF/models/wavlm/modeling_wavlm.py:1010-1024)
+        int64_t Ts[7];
+        wavlm_lengths(arg, Ts);
+        *value = Ts[6] > 0 ? Ts[6] : 0;
+      } else {
+        *value = 1500;  // Whisper pads / truncates every clip to 30 s
+      }
+      return WFL_OK;
     case WFL_QUERY_WORKSPACE_BYTES: *value = static_cast<int64_t>(h->arena_bytes); return WFL_OK;
     case WFL_QUERY_GRAPHS: *value = static_cast<int64_t>(h->graphs.size()); return WFL_OK;
     default: set_error("wfl_query: unknown query %d", what); return WFL_ERR_INVALID_ARGUMENT;
   }
+}
+
+extern "C" int wfl_packed_buffer(wfl_handle* handle, const char* name, const void** dev_ptr, int64_t* bytes) {
+  Handle* h = reinterpret_cast<Handle*>(handle);
+  WFL_CHECK_ARG(h && name && dev_ptr && bytes, "wfl_packed_buffer: null pointer");
+  auto it = h->W.find(name);
+  if (it != h->W.end()) {
+    *dev_ptr = it->second.p;
+    *bytes = static_cast<int64_t>(it->second.bytes);
+    return WFL_OK;
+  }
+  if (strncmp(name, "rel.", 4) == 0) {  // WavLM relative-position bias table of a sequence length already seen
+    auto r = h->rel_tables.find(atoi(name + 4));
+    if (r != h->rel_tables.end()) {
+      *dev_ptr = r->second.p;
+      *bytes = static_cast<int64_t>(r->second.bytes);
+      return WFL_OK;
+    }
+  }
+  if (strncmp(name, "ws.", 3) == 0) {  // a workspace buffer (extent unknown here: bytes = 0)
+    auto w = h->ws.find(name + 3);
+    if (w != h->ws.end()) {
+      *dev_ptr = w->second;
+      *bytes = 0;
+      return WFL_OK;
+    }
+  }
+  set_error("wfl_packed_buffer: no buffer named '%s'", name);
+  return WFL_ERR_INVALID_ARGUMENT;
 }
 
 extern "C" int wfl_forward(wfl_handle* handle, const float* wave_dev, int64_t wave_stride, const int64_t* lang_dev, int32_t B,
@@ -1053,12 +1403,31 @@ extern "C" int wfl_forward(wfl_handle* handle, const float* wave_dev, int64_t wa
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   WFL_CHECK_ARG(h && h->finalized, "wfl_forward: the handle is not finalized");
   WFL_CHECK_ARG(wave_dev && logits_dev && offsets_dev, "wfl_forward: null pointer");
-  WFL_CHECK_ARG(B >= 1 && N >= 1 && wave_stride >= (N < 480000 ? N : 480000), "wfl_forward: bad shape (B %d, N %d)", B, N);
-  if (B > h->arena_batch) {
+  const bool wavlm = h->cfg.encoder_type == WFL_ENCODER_WAVLM;
+  if (wavlm) {
+    WFL_CHECK_ARG(B >= 1 && N >= 1 && wave_stride >= N, "wfl_forward: bad shape (B %d, N %d)", B, N);
+    int64_t Ts[7];
+    wavlm_lengths(N, Ts);
+    WFL_CHECK_ARG(Ts[6] >= 1, "wfl_forward: clip of %d samples is shorter than WavLM's receptive field", N);
+  } else {
+    WFL_CHECK_ARG(B >= 1 && N >= 1 && wave_stride >= (N < 480000 ? N : 480000), "wfl_forward: bad shape (B %d, N %d)", B, N);
+  }
+  if (B > h->arena_batch || (wavlm && N > h->arena_samples)) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &st);
     WFL_CHECK_ARG(st == cudaStreamCaptureStatusNone, "wfl_forward: batch %d exceeds the workspace (max_batch %d) during stream capture", B, h->arena_batch);
-    TRY(ensure_workspace(h, B));
+    TRY(ensure_workspace(h, B, N));
+  }
+  if (wavlm) {  // the bias table is built with synchronous copies: have it resident before any capture
+    const float* tab = nullptr;
+    int64_t Ts[7];
+    wavlm_lengths(N, Ts);
+    if (h->rel_tables.find(static_cast<int>(Ts[6])) == h->rel_tables.end()) {
+      cudaStreamCaptureStatus st0 = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &st0);
+      WFL_CHECK_ARG(st0 == cudaStreamCaptureStatusNone, "wfl_forward: first pass at %d samples during stream capture (run it once uncaptured)", N);
+      TRY(rel_bias_table(h, static_cast<int>(Ts[6]), &tab));
+    }
   }
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &st);
@@ -1137,8 +1506,12 @@ extern "C" int wfl_postprocess(wfl_handle* handle, const float* logits_dev, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   WFL_CHECK_ARG(h && h->finalized && h->n_label_entries == h->L, "wfl_postprocess: finalize the handle and set the labels first");
   WFL_CHECK_ARG(logits_dev && segs_dev && nseg_dev && B >= 1 && T >= 1, "wfl_postprocess: bad argument");
-  WFL_CHECK_ARG(T <= 1500, "wfl_postprocess: %d frames exceed the workspace", T);
-  if (B > h->arena_batch) TRY(ensure_workspace(h, B));
+  if (h->cfg.encoder_type == WFL_ENCODER_WAVLM) {
+    if (B > h->arena_batch || T > h->arena_frames) TRY(ensure_workspace(h, B, (static_cast<int64_t>(T) - 1) * 320 + 400));
+  } else {
+    WFL_CHECK_ARG(T <= 1500, "wfl_postprocess: %d frames exceed the workspace", T);
+    if (B > h->arena_batch) TRY(ensure_workspace(h, B, 480000));
+  }
   int32_t* ids = WS<int32_t>(h, "ids");
   int32_t* ids2 = WS<int32_t>(h, "ids2");
   int32_t* lengths = WS<int32_t>(h, "lengths");

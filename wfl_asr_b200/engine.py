@@ -218,7 +218,8 @@ class Engine:
         pc = "encoder.encoder.pos_conv_embed.conv."
         g = sd[pc + "parametrizations.weight.original0"].float()
         v = sd[pc + "parametrizations.weight.original1"].float()
-        w = v * (g / v.norm(dim=(0, 1), keepdim=True))  # weight_norm(dim=2): [d, d/16, 128]
+        # weight_norm(dim=2): [d, d/16, 128]; folded in fp64 and rounded once (the handle API's C++ packer does the same)
+        w = (v.double() * (g.double() / v.double().norm(dim=(0, 1), keepdim=True))).float()
         bias = sd[pc + "bias"].float()
         G, K = c["pos_groups"], c["pos_k"]
         cg = d // G

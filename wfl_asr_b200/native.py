@@ -42,6 +42,7 @@ def native_config(config, n_labels, precision_high=True, max_batch=0):
     c.lang_emb_dim = m.get("lang_emb_dim", 64)
     c.precision_high = int(precision_high)
     c.max_batch = int(max_batch)
+    c.wavlm_layer_norm = int(a.get("norm") == "layer")
     return c
 
 
@@ -74,6 +75,22 @@ class NativeModel:
         _lib.check(self.lib.wfl_query(self.handle, what, arg, ctypes.byref(v)), "wfl_query")
         return int(v.value)
 
+    def packed(self, name, dtype=torch.uint8, nbytes=None):
+        """Copy of one packed weight by its kernel-side name (diagnostic: wfl_packed_buffer); ``nbytes`` gives the
+        extent for the "ws.<name>" workspace buffers, whose size the handle does not report."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(self.lib.wfl_packed_buffer(self.handle, name.encode(), ctypes.byref(ptr), ctypes.byref(n)), "wfl_packed_buffer")
+        if nbytes is not None:
+            n.value = int(nbytes)
+        if not n.value:
+            return torch.empty(0, dtype=dtype, device=self.dev)
+
+        class _View:  # the handle's memory, seen through the CUDA array interface for the duration of the copy
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+
+        with torch.cuda.device(self.dev):
+            return torch.as_tensor(_View(), device=self.dev).clone().view(dtype)
+
     @torch.no_grad()
     def forward(self, wave, lang_id=None, out=None):
         """wave fp32 [B, N] on the device -> (logits [B, T, L] view of a [B, T, Lp] buffer, offsets [B, T, 2])."""
@@ -81,6 +98,8 @@ class NativeModel:
             raise WflError("NativeModel.forward needs a contiguous-row fp32 CUDA tensor (no CPU path)")
         B, N = wave.shape
         T = self.query(QUERY_FRAMES, N)
+        if T < 1:  # the reference's conv stack raises on such a clip too (TF/models/wavlm/modeling_wavlm.py:703-751)
+            raise WflError(f"clip of {N} samples is shorter than the encoder's receptive field")
         if out is None:
             out = (torch.empty(B, T, self.Lp, device=self.dev), torch.empty(B, T, 2, device=self.dev))
         logits, offsets = out
