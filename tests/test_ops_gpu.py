@@ -457,7 +457,7 @@ def _label_tables(labels):
 
 
 def _segs_from_device(segs, n, phon):
-    raw = segs.cpu().numpy().view(np.dtype([("s", "<f8"), ("e", "<f8"), ("ph", "<i4"), ("pad", "<i4")]))
+    raw = segs.cpu().numpy().view(np.dtype([("s", "<f8"), ("e", "<f8"), ("ph", "<i4"), ("pad", "<i4")])).reshape(-1)
     return [(float(raw["s"][i]), float(raw["e"][i]), phon[int(raw["ph"][i])]) for i in range(n)]
 
 
@@ -517,6 +517,43 @@ def test_bio_decode_merge_lab_golden(golden):
                 ops.htk_times(out[i], oc[i], s_h, e_h)
                 lab = "".join(f"{a} {b} {p}\n" for a, b, (_, _, p) in zip(s_h.cpu().tolist(), e_h.cpu().tolist(), got))
                 assert lab == recs[i]["lab"][mode]
+
+
+def test_bio_decode_random_sequences_match_oracle():
+    """The multi-warp scan (16 ranges per clip) against the oracle state machine on adversarial sequences: ragged
+    lengths around the group / range edges, long runs that stay open across many ranges, stretches of ignored
+    tags (REF/utils.py:27-28 skips anything that is not O / B- / I-) between an I- tag and its predecessor."""
+    from oracle import postproc_oracle as po
+    labels = ["O", "SP", "<unk>"] + [f"{p}-{n}" for n in ("a", "b", "k", "sh") for p in ("B", "I")]
+    phon, kind, ph = _label_tables(labels)
+    lens = [0, 1, 31, 32, 33, 95, 96, 97, 511, 512, 513, 1499, 1500, 2999, 3000]
+    rng = np.random.default_rng(7)
+    styles = []
+    for i, n in enumerate(lens * 3):
+        style = i // len(lens)
+        if style == 0:    # every tag equally likely
+            ids = rng.integers(0, len(labels), n)
+        elif style == 1:  # long runs: one tag held for 1..400 frames
+            ids = np.concatenate([np.full(rng.integers(1, 400), rng.integers(0, len(labels))) for _ in range(n // 2 + 1)])[:n]
+        else:             # mostly ignored tags with rare real ones
+            ids = np.where(rng.random(n) < 0.03, rng.integers(0, len(labels), n), rng.integers(1, 3, n))
+        styles.append(ids.astype(np.int32))
+    stride = max(lens)
+    B = len(styles)
+    ids_t = torch.zeros(B, stride, dtype=torch.int32)
+    for i, a in enumerate(styles):
+        ids_t[i, :len(a)] = torch.from_numpy(a)
+    offs = torch.from_numpy(rng.random((B, stride, 2), dtype=np.float32))
+    ln = torch.tensor([len(a) for a in styles], dtype=torch.int32, device=DEV)
+    for with_off in (True, False):
+        segs = torch.zeros(B, stride, 24, dtype=torch.uint8, device=DEV)
+        nseg = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+        ops.bio_decode(ids_t.to(DEV), offs.to(DEV) if with_off else None, ln, kind, ph, 0.02, None, segs, nseg)
+        counts = nseg.cpu().tolist()
+        for i, a in enumerate(styles):
+            want = po.decode_bio_tags([labels[j] for j in a], 0.02, offs[i, :len(a)].numpy() if with_off else None)
+            got = _segs_from_device(segs[i], counts[i], phon)
+            assert got == [(s, e, p) for s, e, p in want], (i, len(a), with_off)
 
 
 def test_chunked_merge_golden(golden):

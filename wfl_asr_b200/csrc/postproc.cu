@@ -101,49 +101,122 @@ __device__ __forceinline__ double seg_time(int idx, const float* off, int which,
 }
 
 constexpr int kBioMaxLabelsSmem = 1024;
+constexpr int kBioWarps = 16;
 
-__global__ void __launch_bounds__(32) bio_decode_kernel(const int32_t* __restrict__ ids, const float* __restrict__ offsets,
-                                                        const int32_t* __restrict__ lengths, int64_t clip_stride,
-                                                        const int8_t* __restrict__ label_kind,
-                                                        const int32_t* __restrict__ label_ph, int n_labels, double fd,
-                                                        const double* __restrict__ time_shift,
-                                                        wfl_segment* __restrict__ segs, int32_t* __restrict__ nseg) {
+// One CTA of kBioWarps warps per clip; warp w owns a contiguous range of 32-frame groups.  REF/utils.py:10-74 is a
+// left-to-right scan whose state is (phoneme of the last B/I/O tag, the open run); it splits over ranges as
+//   pass 1: the phoneme each range hands to the next one (last non-OTHER tag of the range)      -> carry in per range
+//   pass 2: with the carry known, how many runs open in the range and where its first boundary is -> slot base per range
+//   pass 3: the single-warp scan of the range, writing its runs at their global slots; a run still open at the end of
+//           the range closes at the first boundary of a later range (or at the last frame, REF/utils.py:63-72).
+// Slot order = order of opening, so the records are the ones the one-warp-per-clip scan produced, bit for bit; the
+// serial chain per clip drops from T / 32 group steps to ~T / (32 kBioWarps) per pass.
+__global__ void __launch_bounds__(kBioWarps * 32) bio_decode_kernel(
+    const int32_t* __restrict__ ids, const float* __restrict__ offsets, const int32_t* __restrict__ lengths, int64_t clip_stride,
+    const int8_t* __restrict__ label_kind, const int32_t* __restrict__ label_ph, int n_labels, double fd,
+    const double* __restrict__ time_shift, wfl_segment* __restrict__ segs, int32_t* __restrict__ nseg) {
   const int c = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int T = lengths[c];
   const int32_t* cid = ids + c * clip_stride;
   const float* off = offsets != nullptr ? offsets + 2 * c * clip_stride : nullptr;
   wfl_segment* out = segs + c * clip_stride;
   const double shift = time_shift != nullptr ? time_shift[c] : 0.0;
   const bool do_shift = time_shift != nullptr;
-
-  int carry_ph = -1;      // phoneme open after the last non-OTHER tag seen so far (-1: none)
-  int pending_slot = -1;  // slot of the run still open at the end of the previous group
-  int count = 0;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // The loop is a serial chain over groups of 32 frames; its only long-latency part is ids -> label tables.  The
-  // tables are staged in shared memory (when they fit) and the ids of the NEXT group are requested one iteration early.
   __shared__ int8_t kind_sm[kBioMaxLabelsSmem];
   __shared__ int32_t ph_sm[kBioMaxLabelsSmem];
+  __shared__ int last_ph_sm[kBioWarps];      // pass 1: phoneme after the range's last non-OTHER tag (-1: none open)
+  __shared__ int has_valid_sm[kBioWarps];    //         whether the range holds a non-OTHER tag at all
+  __shared__ int n_open_sm[kBioWarps];       // pass 2: runs opened inside the range
+  __shared__ int first_bound_sm[kBioWarps];  //         frame index of the range's first boundary (-1: none)
   const bool tables_in_smem = n_labels <= kBioMaxLabelsSmem;
-  if (tables_in_smem) {
-    for (int l = lane; l < n_labels; l += 32) {
+  if (tables_in_smem)
+    for (int l = threadIdx.x; l < n_labels; l += kBioWarps * 32) {
       kind_sm[l] = label_kind[l];
       ph_sm[l] = label_ph[l];
     }
-    __syncwarp();
-  }
-  int id_next = lane < T ? cid[lane] : -1;
-  for (int g0 = 0; g0 < T; g0 += 32) {
-    const int i = g0 + lane;
-    const int id = id_next;
-    id_next = i + 32 < T ? cid[i + 32] : -1;
-    int kind = WFL_TAG_OTHER, ph = -1;
-    if (i < T && id >= 0 && id < n_labels) {
-      kind = tables_in_smem ? kind_sm[id] : label_kind[id];
-      ph = tables_in_smem ? ph_sm[id] : label_ph[id];
+  __syncthreads();
+
+  const int groups = (T + 31) / 32;
+  const int per_warp = (groups + kBioWarps - 1) / kBioWarps;
+  const int g_begin = min(warp * per_warp, groups) * 32, g_end = min((warp + 1) * per_warp, groups) * 32;
+
+  auto classify = [&](int i, int& kind, int& ph) {
+    kind = WFL_TAG_OTHER;
+    ph = -1;
+    if (i < T) {
+      const int id = cid[i];
+      if (id >= 0 && id < n_labels) {
+        kind = tables_in_smem ? kind_sm[id] : label_kind[id];
+        ph = tables_in_smem ? ph_sm[id] : label_ph[id];
+      }
     }
+  };
+
+  // ---- pass 1: what the range hands over
+  {
+    int last_ph = -1, has_valid = 0;
+    for (int g0 = g_end - 32; g0 >= g_begin; g0 -= 32) {  // backwards: the first group with a valid tag decides
+      int kind, ph;
+      classify(g0 + lane, kind, ph);
+      const unsigned m_valid = __ballot_sync(0xffffffffu, kind != WFL_TAG_OTHER);
+      if (m_valid) {
+        const int ph_eff = kind == WFL_TAG_O ? -1 : ph;
+        last_ph = __shfl_sync(0xffffffffu, ph_eff, 31 - __clz(m_valid));
+        has_valid = 1;
+        break;
+      }
+    }
+    if (lane == 0) {
+      last_ph_sm[warp] = last_ph;
+      has_valid_sm[warp] = has_valid;
+    }
+  }
+  __syncthreads();
+  int carry_in = -1;
+  for (int w = warp - 1; w >= 0; --w)
+    if (has_valid_sm[w]) {
+      carry_in = last_ph_sm[w];
+      break;
+    }
+
+  // ---- pass 2: opens and first boundary of the range
+  {
+    int carry_ph = carry_in, n_open = 0, first_bound = -1;
+    for (int g0 = g_begin; g0 < g_end; g0 += 32) {
+      int kind, ph;
+      classify(g0 + lane, kind, ph);
+      const int ph_eff = (kind == WFL_TAG_O || kind == WFL_TAG_OTHER) ? -1 : ph;
+      const unsigned m_valid = __ballot_sync(0xffffffffu, kind != WFL_TAG_OTHER);
+      const unsigned below = m_valid & lt_mask;
+      const int ph_from_lane = __shfl_sync(0xffffffffu, ph_eff, below ? 31 - __clz(below) : 0);
+      const int prev_ph = below ? ph_from_lane : carry_ph;
+      const bool open = (kind == WFL_TAG_B) || (kind == WFL_TAG_I && ph != prev_ph);
+      const unsigned m_open = __ballot_sync(0xffffffffu, open);
+      const unsigned m_bound = __ballot_sync(0xffffffffu, (kind == WFL_TAG_O) || open);
+      n_open += __popc(m_open);
+      if (first_bound < 0 && m_bound) first_bound = g0 + __ffs(m_bound) - 1;
+      if (m_valid) carry_ph = __shfl_sync(0xffffffffu, ph_eff, 31 - __clz(m_valid));
+    }
+    if (lane == 0) {
+      n_open_sm[warp] = n_open;
+      first_bound_sm[warp] = first_bound;
+    }
+  }
+  __syncthreads();
+  int count = 0;
+  for (int w = 0; w < warp; ++w) count += n_open_sm[w];
+
+  // ---- pass 3: the scan of the range, writing at global slots
+  int carry_ph = carry_in;
+  int pending_slot = -1;  // slot of the run still open at the end of the previous group
+  for (int g0 = g_begin; g0 < g_end; g0 += 32) {
+    const int i = g0 + lane;
+    int kind, ph;
+    classify(i, kind, ph);
     const int ph_eff = (kind == WFL_TAG_O || kind == WFL_TAG_OTHER) ? -1 : ph;
     const unsigned m_valid = __ballot_sync(0xffffffffu, kind != WFL_TAG_OTHER);
     // phoneme that is "current" just before this frame
@@ -194,12 +267,18 @@ __global__ void __launch_bounds__(32) bio_decode_kernel(const int32_t* __restric
     }
   }
   if (pending_slot >= 0 && lane == 0) {
-    // REF/utils.py:63-72: run still open at the end closes at len(tags) - 1
-    double e = seg_time(T - 1, off, 1, fd);
+    // closes at the first boundary of a later range, else (REF/utils.py:63-72) at len(tags) - 1
+    int e_idx = T - 1;
+    for (int w = warp + 1; w < kBioWarps; ++w)
+      if (first_bound_sm[w] >= 0) {
+        e_idx = first_bound_sm[w];
+        break;
+      }
+    double e = seg_time(e_idx, off, 1, fd);
     if (do_shift) e = __dadd_rn(e, shift);
     out[pending_slot].end = e;
   }
-  if (lane == 0) nseg[c] = count;
+  if (warp == kBioWarps - 1 && lane == 0) nseg[c] = count;
 }
 
 // ------------------------------------------------------------------------------------------ merge
@@ -320,7 +399,7 @@ extern "C" int wfl_bio_decode(const int32_t* ids, const float* offsets, const in
   WFL_CHECK_ARG(ids && lengths && label_kind && label_ph && segs && nseg, "wfl_bio_decode: null pointer");
   WFL_CHECK_ARG(n_labels >= 1, "wfl_bio_decode: empty label table");
   if (n_clips <= 0) return WFL_OK;
-  bio_decode_kernel<<<n_clips, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  bio_decode_kernel<<<n_clips, kBioWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       ids, offsets, lengths, clip_stride, label_kind, label_ph, n_labels, frame_duration, time_shift, segs, nseg);
   WFL_CUDA(cudaGetLastError());
   return WFL_OK;
