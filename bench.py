@@ -191,12 +191,13 @@ def run_ours(args, rank, world, local_rank):
     # the same clip through the handle-level C ABI alone (csrc/handle.cu: wfl_forward + wfl_postprocess, its own CUDA
     # graph; no engine.py, no Python launch loop): pinned host waveform -> device -> segments on the host
     lat_native = None
-    if cfg["model"]["encoder_type"] == "whisper":
-        from wfl_asr_b200.native import NativeModel
+    if cfg["model"]["encoder_type"] in ("whisper", "wavlm"):
+        from wfl_asr_b200.native import QUERY_FRAMES, NativeModel
         nm = NativeModel(cfg, labels, {k: v.detach().cpu() for k, v in model.state_dict().items()}, dev, max_batch=1)
         side = torch.cuda.Stream(dev)
         wave1 = torch.empty(1, one.shape[1], device=dev)
-        out1 = (torch.empty(1, 1500, nm.Lp, device=dev), torch.empty(1, 1500, 2, device=dev))
+        T1 = nm.query(QUERY_FRAMES, one.shape[1])
+        out1 = (torch.empty(1, T1, nm.Lp, device=dev), torch.empty(1, T1, 2, device=dev))
         latn = []
         with torch.cuda.stream(side):
             for i in range(25):
@@ -296,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3), "segments_per_step": n_seg / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-        "latency_p50_ms": {"value": round(lat_p50, 3), "what": "one 30 s clip, batch 1, pinned host waveform -> python "
+        "latency_p50_ms": {"value": round(lat_p50, 3), "what": f"one {wl['seconds']:g} s clip, batch 1, pinned host waveform -> python "
                            "segments (H2D + forward + post-processing + D2H), median of 20 synchronous calls",
                            "handle_c_abi": None if lat_native is None else round(lat_native, 3),
                            "handle_c_abi_what": "same clip through wfl_forward + wfl_postprocess of the handle-level C ABI only"},
