@@ -5,7 +5,7 @@ import torch
 from wfl_asr_b200 import ops
 from wfl_asr_b200.frontend import whisper_frontend_constants
 dev = torch.device("cuda:0")
-B, T, d = int(os.environ.get("PROF_B", "32")), 1500, 512
+B, T, d = int(os.environ.get("PROF_B", "32")), int(os.environ.get("PROF_T", "1500")), int(os.environ.get("PROF_D", "512"))
 which = sys.argv[1:] or ["attn64"]
 reps = int(os.environ.get("REPS", "2"))
 g = torch.Generator().manual_seed(0)
@@ -18,7 +18,16 @@ def t_ms(fn):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 for w in which:
-    if w.startswith("attn"):
+    if w == "attn64b":  # WavLM: head dim 64 with the gated relative-position bias (PROF_B / PROF_T / PROF_D)
+        H = d // 64
+        qkv = (torch.randn(B, T, 3 * d, generator=g) * 0.5).to(dev).half()
+        out = torch.empty(B, T, d, device=dev, dtype=torch.float16)
+        tab = (torch.randn(H, 2 * T - 1, generator=g) * 0.5).to(dev)
+        gate = (torch.rand(B, H, T, generator=g) * 2).to(dev)
+        ms = t_ms(lambda: ops.attention(qkv, out, B=B, T=T, H=H, hd=64, scale=0.125, q_col=0, k_col=d, v_col=2 * d,
+                                        rel_bias=tab, gate=gate))
+        print(f"{w} B{B} T{T} H{H} ({os.environ.get('WFL_ATTN64', 'default')}): {ms:.3f} ms  {4.0 * T * T * d * B / ms / 1e9:.1f} TFLOP/s")
+    elif w.startswith("attn"):
         hd = int(w[4:]); H = d // hd if hd <= 256 else 2
         dd = H * hd
         qkv = (torch.randn(B, T, 3 * dd, generator=g) * 0.5).to(dev).half()

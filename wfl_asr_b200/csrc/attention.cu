@@ -89,7 +89,10 @@ struct AttnParams {
   const float* gate;      // [B][H][T] or null
 };
 
-template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64>
+// kBiasSmem: the query tile's window of the relative-position table (T + 127 entries: row r of the tile, key k ->
+// entry k + 127 - r) is staged in shared memory behind the barriers once per CTA, so the per-score bias fetch is an
+// LDS at [row base + immediate] instead of a clamped LDG (0.198 -> see profiles/README.md at B 16 x H 16 x T 799).
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64, bool kBiasSmem = false>
 __global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES, kPTmem, KT>::kCtasPerSm))
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                  const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
@@ -119,6 +122,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint64_t* p_full = s_empty + S_BUFS;          // [2]
   uint64_t* pv_done = p_full + 2;               // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* bias_tab = reinterpret_cast<float*>(smem + Cfg::kSmemBytes);  // [n_kv * KT + 128] when kBiasSmem
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -279,7 +283,20 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (has_bias) {
       const int qi = q_idx < p.T ? q_idx : p.T - 1;
       gate_l2 = p.gate[(static_cast<int64_t>(b) * p.H + h) * p.T + qi] * kLog2e;
-      bias_row = p.rel_bias + static_cast<int64_t>(h) * (2 * p.T - 1) + (p.T - 1 - qi);  // + k
+      if constexpr (kBiasSmem) {
+        // entry i of the window = table index (T - 1) - (q0 + 127) + i; rows past T and keys past T read zeros
+        const float* tab = p.rel_bias + static_cast<int64_t>(h) * (2 * p.T - 1);
+        const int first = (p.T - 1) - (q0 + 127);
+        const int n_tab = n_kv * KV_TILE + 128;
+        for (int i = threadIdx.x - 128; i < n_tab; i += kAttnThreads - 128) {
+          const int idx = first + i;
+          bias_tab[i] = (idx >= 0 && idx <= 2 * p.T - 2) ? __ldg(tab + idx) : 0.f;
+        }
+        asm volatile("bar.sync 6, 256;" ::: "memory");  // the eight softmax warps
+        bias_row = bias_tab + (127 - r);  // + k
+      } else {
+        bias_row = p.rel_bias + static_cast<int64_t>(h) * (2 * p.T - 1) + (p.T - 1 - qi);  // + k
+      }
     }
     float m_used = -INFINITY;
     float l_sum = 0.f;  // this warp's 32 columns only; the two halves are added in the epilogue
@@ -313,10 +330,17 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         constexpr bool kBias = decltype(bias_c)::value;
         const float sc = kBias ? 1.0f : p.scale_log2;
         if constexpr (kBias) {
+          if constexpr (kBiasSmem) {
+            const float* br = bias_row + kv0;  // the window is padded: no clamp, keys past T are masked below
 #pragma unroll
-          for (int i = 0; i < CW; ++i) {
-            const int k = min(kv0 + i, p.T - 1);
-            v[i] = __float_as_uint(fmaf(gate_l2, __ldg(bias_row + k), __uint_as_float(v[i]) * p.scale_log2));
+            for (int i = 0; i < CW; ++i)
+              v[i] = __float_as_uint(fmaf(gate_l2, br[i], __uint_as_float(v[i]) * p.scale_log2));
+          } else {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+              const int k = min(kv0 + i, p.T - 1);
+              v[i] = __float_as_uint(fmaf(gate_l2, __ldg(bias_row + k), __uint_as_float(v[i]) * p.scale_log2));
+            }
           }
         }
         if (tail) {
@@ -466,7 +490,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 }
 
-template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64>
+// shared-memory window of the relative-position table per CTA, and the most a CTA may take with two CTAs per SM
+constexpr int kBiasSmemLimit = 113 * 1024;
+static int bias_window_bytes(int T, int KT) { return (((T + KT - 1) / KT) * KT + 128) * 4; }
+
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64, bool kBiasSmem = false>
 static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int B, int T, int H,
                             const AttnParams& p, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                             cudaStream_t stream) {
@@ -492,10 +520,12 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias, KT>;
+  auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias, KT, kBiasSmem>;
+  const int smem_bytes = Cfg::kSmemBytes + (kBiasSmem ? bias_window_bytes(T, KT) : 0);
   static PerDeviceOnce configured;  // per instantiation and device
   if (configured.needed()) {
-    WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kBiasSmem ? kBiasSmemLimit : Cfg::kSmemBytes));
     configured.done();
   }
   dim3 grid((T + 127) / 128, H, B);
@@ -503,7 +533,7 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
     static const bool no_pdl = getenv("WFL_NO_PDL_ATTN") != nullptr;
     pdl_family_off() = no_pdl;
   }
-  WFL_CUDA(launch_pdl(kern, grid, dim3(kAttnThreads), Cfg::kSmemBytes, stream, mq, mkv, mo, p));
+  WFL_CUDA(launch_pdl(kern, grid, dim3(kAttnThreads), smem_bytes, stream, mq, mkv, mo, p));
   return WFL_OK;
 }
 
@@ -547,9 +577,15 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
   }
   switch (hd) {
     case 64:
-      if (rel_bias != nullptr)
+      if (rel_bias != nullptr) {
+        // the table window in shared memory when it fits beside two resident CTAs (T <= ~11 000 frames = 230 s); the
+        // choice depends on the clip length only, and both variants evaluate the same expression
+        if (AttnCfg<64, 3, true>::kSmemBytes + bias_window_bytes(T, 64) <= kBiasSmemLimit && getenv("WFL_ATTN_BIAS_LDG") == nullptr)
+          return launch_attention<64, 3, true, true, 64, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
+                                                               out_batch_stride, stream);
         return launch_attention<64, 3, true, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                                    out_batch_stride, stream);
+      }
       return launch_attention<64, 3, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                                   out_batch_stride, stream);
     case 256:
