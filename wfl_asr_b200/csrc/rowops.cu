@@ -10,8 +10,11 @@ namespace wfl {
 constexpr int kLnMaxVecLimit = 12;  // float4 per lane -> d <= 1536
 
 // K8. nn.LayerNorm semantics (TORCH layer_norm: biased variance, eps inside the sqrt), fp32 statistics.
+// Wide rows (d > 768): the register prefetch of the next row would push the kernel to 152 registers = one block of 8
+// warps per SM (ncu: 12.5 % occupancy, 3.5 TB/s at d 1280); those widths keep one row per warp in registers and get
+// their memory-level parallelism from 2-3 resident blocks instead (profiles/README.md).
 template <int kLnMaxVec>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t rows, int d,
+__global__ void __launch_bounds__(256, (kLnMaxVec <= 4 ? 3 : (kLnMaxVec <= 6 ? 2 : (kLnMaxVec <= 8 ? 3 : 2)))) layernorm_kernel(const float* __restrict__ x, int64_t rows, int d,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
                                                         const float* __restrict__ gamma2,
@@ -28,8 +31,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int64_t warp_stride = static_cast<int64_t>(gridDim.x) * 8;
   int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float4 nxt[kLnMaxVec];
-  {
+  constexpr bool kPrefetch = kLnMaxVec <= 6;
+  float4 nxt[kPrefetch ? kLnMaxVec : 1];
+  if constexpr (kPrefetch) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * d);
 #pragma unroll
     for (int i = 0; i < kLnMaxVec; ++i) {
@@ -44,10 +48,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < nvec) {
-      v[i] = nxt[i];
+      if constexpr (kPrefetch) v[i] = nxt[i];
+      else v[i] = reinterpret_cast<const float4*>(x + row * d)[idx];
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
+  if constexpr (kPrefetch)
   if (row + warp_stride < rows) {
     const float4* xr = reinterpret_cast<const float4*>(x + (row + warp_stride) * d);
 #pragma unroll
