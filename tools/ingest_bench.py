@@ -80,9 +80,16 @@ def measure(files=256, seconds=30.0, workers=8, workload="cfg2", dev=None):
         infer.infer_folder(wav_dir, *args, output_dir=os.path.join(tmp, "warm"), **kw)
         torch.cuda.synchronize(dev)
         t = time.perf_counter()
+        if os.environ.get("WFL_INGEST_PROFILE"):
+            import cProfile, pstats
+            pr = cProfile.Profile()
+            pr.enable()
         res = infer.infer_folder(wav_dir, *args, output_dir=os.path.join(tmp, "labs"), **kw)
         torch.cuda.synchronize(dev)
         dt_lab = time.perf_counter() - t
+        if os.environ.get("WFL_INGEST_PROFILE"):
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
         n_lab = len([f for f in os.listdir(os.path.join(tmp, "labs")) if f.endswith(".lab")])
         assert n_lab == files and len(res) == files
         return {"files": files, "clip_seconds": seconds, "audio_seconds": audio_s, "format": "RIFF/WAVE PCM16 mono 16 kHz",
