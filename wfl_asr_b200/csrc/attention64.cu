@@ -95,7 +95,73 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& e0, float& e1) {
 #define WFL_A64_POLY_EVERY 0  // every n-th pair of exponentials goes to the FMA pipe (0 = none)
 #endif
 
-template <bool kHasBias>
+// 16-lane tensor-memory shapes (tools/micro/tmem_shapes.cu confirms the mapping on sm_100a): a warp reads 16 rows x 128
+// fp32 columns as .16x256b.x16 -- thread t holds rows t/4 and t/4 + 8, and of every 8-column group g the columns
+// 8g + 2 (t % 4) + {0, 1}: v[4g + 0..1] = first row, v[4g + 2..3] = second row -- so a row lives in ONE quad of lanes
+// and its maximum / sum need two shuffles instead of a shared-memory exchange between warps.  Packed f16 pairs go back
+// as .16x128b (column 4g + t % 4 of rows t/4, t/4 + 8 = registers 2g, 2g + 1): exactly the pairs the thread holds.
+__device__ __forceinline__ void tmem_ld_16x256b_x16(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// 16 registers starting at OFF of a 64-entry array -> 32 packed columns (.16x128b.x8) of the warp's 16 rows
+template <int OFF>
+__device__ __forceinline__ void tmem_st_16x128b_x8_of64(uint32_t taddr, const uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[OFF + 0]), "r"(v[OFF + 1]), "r"(v[OFF + 2]), "r"(v[OFF + 3]), "r"(v[OFF + 4]), "r"(v[OFF + 5]), "r"(v[OFF + 6]), "r"(v[OFF + 7]), "r"(v[OFF + 8]), "r"(v[OFF + 9]), "r"(v[OFF + 10]), "r"(v[OFF + 11]), "r"(v[OFF + 12]), "r"(v[OFF + 13]), "r"(v[OFF + 14]), "r"(v[OFF + 15])
+      : "memory");
+}
+
+// kGen 2: two softmax warps per 32-row quarter split the tile's COLUMNS (thread = half a row; row maxima meet in shared
+//         memory under a 64-thread named barrier; exponentials start speculatively before the exchange).
+// kGen 3: the two warps split the quarter's ROWS (16 each) and read S in the 16-lane shape, a row = one quad of lanes:
+//         maxima and sums by shuffle, no exchange buffer, no named barrier, S goes back to the tensor core right after
+//         the row maximum (before any exponential), each warp stores its own 16 output rows.
+template <bool kHasBias, int kGen>
 __global__ void __launch_bounds__(kA64Threads, 1)
 attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out,
                    const A64Params p) {
@@ -145,7 +211,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 8);  // the eight output-storing lanes of an item (2 query tiles x 4 lane quarters)
+      mbar_init(&q_empty[i], kGen == 3 ? 16 : 8);  // the output-storing lanes of an item (2 query tiles x 4 quarters [x 2 row halves])
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 8);  // the eight softmax warps of the query tile
       mbar_init(&o_free[i], 8);
@@ -317,7 +383,8 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
 #endif
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const int k16 = (kk >> 1) * 4 + sub * 2 + (kk & 1);  // 16-key step inside the tile
+              // 16-key step inside the tile (kGen 2: sub-block 0 = keys [0,32) + [64,96); kGen 3: keys [0,64))
+              const int k16 = kGen == 3 ? sub * 4 + kk : (kk >> 1) * 4 + sub * 2 + (kk & 1);
               // B = V, MN-major: one key row = 64 head columns = 128 B; 8 rows = one 1024 B swizzle atom (SBO)
               const uint64_t db = umma_smem_desc(v_addr + k16 * 2048, kA64KvBytes, 1024);
               // A = P from tensor memory: 16 keys = 8 packed 32-bit columns per instruction
@@ -334,6 +401,184 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
       }
     }
   }
+  } else if constexpr (kGen == 3) {
+    // ============================== softmax / correction / epilogue, row-quad form ==============================
+    const int qt = (warp - 4) >> 3;           // query tile
+    const int rhalf = ((warp - 4) >> 2) & 1;  // which 16 of the quarter's 32 rows
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may address
+    const int row_base = quarter * 32 + rhalf * 16;
+    const int r0 = row_base + (lane >> 2);    // this thread's first row inside the query tile (the second is r0 + 8)
+    const int c0 = (lane & 3) * 2;            // its columns inside every 8-column group: c0, c0 + 1
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(row_base) << 16);
+    const uint32_t s_addr = lane_addr + kA64ColS + qt * 128;
+    const uint32_t p_addr = lane_addr + kA64ColP + qt * 64;
+    const uint32_t o_addr = lane_addr + kA64ColO + qt * 64;
+    const float sc = p.scale_log2;
+    int gq = 0, n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      int b, h, q0, nq;
+      item_coords(item, b, h, q0, nq);
+      const int buf = n & 1;
+      if (qt >= nq) continue;
+      float m_used0 = -INFINITY, m_used1 = -INFINITY;  // exponent offsets of the two rows
+      float l_sum0 = 0.f, l_sum1 = 0.f;                // this thread's columns only; the quad meets in the epilogue
+      for (int j = 0; j < n_kv; ++j) {
+#ifdef WFL_A64_TRACE
+        const bool trace_on = blockIdx.x == 5 && n == 1;
+#endif
+        const int g = gq + j;
+        const bool tail = (j + 1) * kA64Kv > p.T;  // CTA-uniform
+        A64_TRACE(0);
+#ifdef WFL_A64_SPIN_SFULL
+        mbar_wait_spin(&s_full[qt], g & 1);
+#else
+        mbar_wait(&s_full[qt], g & 1);
+#endif
+        A64_TRACE(1);
+        tc_fence_after();
+        uint32_t v[64];
+        tmem_ld_16x256b_x16(s_addr, v);
+        tmem_ld_wait();
+#ifndef WFL_A64_LATE_SEMPTY
+        // the scores are in registers and nothing below reads them from tensor memory again (no redo path in this
+        // form): S_qt goes back to the tensor core at once, Q K^T of the next tile runs beside the whole softmax
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[qt]);
+#endif
+        if (tail) {
+          const int valid = p.T - j * kA64Kv - c0;  // column 8 gg + (e & 1) of this thread is a key iff it is < valid
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if ((i >> 2) * 8 + (i & 1) >= valid) v[i] = 0xff800000u;  // -inf
+        }
+        A64_TRACE(2);
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // [row][chain]
+#pragma unroll
+        for (int gg = 0; gg < 16; ++gg) {
+          mx[gg & 1] = fmax3(mx[gg & 1], __uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]));
+          mx[2 + (gg & 1)] = fmax3(mx[2 + (gg & 1)], __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
+        }
+        float m0 = fmaxf(mx[0], mx[1]), m1 = fmaxf(mx[2], mx[3]);
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+#ifdef WFL_A64_LATE_SEMPTY
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[qt]);
+#endif
+        A64_TRACE(3);
+        const float m_new0 = fmaxf(m_used0, m0 * sc), m_new1 = fmaxf(m_used1, m1 * sc);
+        const bool grow0 = m_new0 > m_used0 + kA64Rescale, grow1 = m_new1 > m_used1 + kA64Rescale;  // true on an item's first tile
+        if (__any_sync(0xffffffffu, grow0 || grow1)) {
+          if (j > 0) {
+            // O must be quiescent: every P V of the previous tile has retired
+            mbar_wait(&pv_done[qt * 2 + 1], (g - 1) & 1);
+            tc_fence_after();
+            const float f0 = grow0 ? ex2_ftz(m_used0 - m_new0) : 1.0f, f1 = grow1 ? ex2_ftz(m_used1 - m_new1) : 1.0f;
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 32) {  // in two halves: the 64 scores stay in registers beside it
+              uint32_t o[16];
+              tmem_ld_16x256b_x4(o_addr + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * ((i & 2) ? f1 : f0));
+              tmem_st_16x256b_x4(o_addr + c, o);
+            }
+            l_sum0 *= f0;
+            l_sum1 *= f1;
+          }
+          if (grow0) m_used0 = m_new0;
+          if (grow1) m_used1 = m_new1;
+        }
+        const uint64_t sc2 = pk2(sc, sc), negm0 = pk2(-m_used0, -m_used0), negm1 = pk2(-m_used1, -m_used1);
+        uint64_t sum0 = pk2(0.f, 0.f), sum1 = pk2(0.f, 0.f);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          // keys [64 sub, 64 sub + 64): exponentials, packed IN PLACE (group gg: v[4gg..4gg+3] -> v[2gg], v[2gg+1])
+#pragma unroll
+          for (int g8 = 0; g8 < 8; ++g8) {
+            const int gg = sub * 8 + g8;
+            float a0, a1, a2, a3;
+            upk2(fma2(pk2u(v[4 * gg], v[4 * gg + 1]), sc2, negm0), a0, a1);
+            upk2(fma2(pk2u(v[4 * gg + 2], v[4 * gg + 3]), sc2, negm1), a2, a3);
+#ifdef WFL_A64_NOEXP
+            const float e0 = fmaf(a0, 1e-3f, 1.0f), e1 = fmaf(a1, 1e-3f, 1.0f), e2 = fmaf(a2, 1e-3f, 1.0f), e3 = fmaf(a3, 1e-3f, 1.0f);
+#else
+            const float e0 = ex2_ftz(a0), e1 = ex2_ftz(a1), e2 = ex2_ftz(a2), e3 = ex2_ftz(a3);
+#endif
+            sum0 = add2(sum0, pk2(e0, e1));
+            sum1 = add2(sum1, pk2(e2, e3));
+            v[2 * gg] = pack_f16(e0, e1);
+            v[2 * gg + 1] = pack_f16(e2, e3);
+          }
+          A64_TRACE(4 + sub * 2);
+          // P_qt is single-buffered: the P V products of the previous tile must have retired before it is overwritten
+          // (ONE wait covers both sub-blocks: they are issued in order by one thread); the first 64 keys' exponentials
+          // above ran beside those products
+          if (sub == 0 && g > 0) {
+            // (an early non-blocking test of this barrier and of the next tile's s_full, consumed here, measured
+            // slower: 0.238 against 0.225 ms -- the extra live registers spill)
+            mbar_wait(&pv_done[qt * 2 + 1], (g - 1) & 1);
+            tc_fence_after();
+          }
+          if (sub == 0) tmem_st_16x128b_x8_of64<0>(p_addr, v);
+          else tmem_st_16x128b_x8_of64<16>(p_addr + 32, v);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[qt * 2 + sub]);
+          A64_TRACE(5 + sub * 2);
+        }
+        float s0, s1, s2, s3;
+        upk2(sum0, s0, s1);
+        upk2(sum1, s2, s3);
+        l_sum0 += s0 + s1;
+        l_sum1 += s2 + s3;
+      }
+      gq += n_kv;
+
+      // ---- epilogue of the item: O / l -> f16 -> this warp's 16 rows of the item's (dead) Q tile -> TMA store
+      float l0 = l_sum0 + __shfl_xor_sync(0xffffffffu, l_sum0, 1), l1 = l_sum1 + __shfl_xor_sync(0xffffffffu, l_sum1, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      mbar_wait(&pv_done[qt * 2 + 1], (gq - 1) & 1);
+      tc_fence_after();
+      const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+      uint8_t* tile = q_smem + (buf * 2 + qt) * kA64QTile;
+      {
+        uint32_t o[32];
+        tmem_ld_16x256b_x8(o_addr, o);
+        tmem_ld_wait();
+        // O_qt is in registers: the next item's first P V may overwrite it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[qt]);
+        uint8_t* row0 = tile + r0 * 128 + (lane & 3) * 4;  // rows r0 and r0 + 8 share (r & 7), i.e. the swizzle phase
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) {
+          const int off = (gg ^ (r0 & 7)) << 4;  // 16-byte chunk gg = columns 8 gg .. 8 gg + 7 (f16)
+          *reinterpret_cast<uint32_t*>(row0 + off) = pack_f16(__uint_as_float(o[4 * gg]) * inv0, __uint_as_float(o[4 * gg + 1]) * inv0);
+          *reinterpret_cast<uint32_t*>(row0 + 8 * 128 + off) =
+              pack_f16(__uint_as_float(o[4 * gg + 2]) * inv1, __uint_as_float(o[4 * gg + 3]) * inv1);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (q0 + qt * 128 + row_base < p.T) {
+          tma_store_3d(&map_out, tile + row_base * 128, h * 64, q0 + qt * 128 + row_base, b);
+          tma_commit_group();
+          tma_wait_group_read<0>();  // the staging rows have been read: the buffer may take the next item's Q
+        }
+        // (when the item has no second query tile, tile 0's warps make its arrivals too: warps without work for an item
+        // run ahead, and their own arrivals would complete a LATER phase of this barrier early)
+        mbar_arrive_cnt(&q_empty[buf], nq == 1 ? 2u : 1u);
+      }
+    }
+    if (lane == 0) tma_wait_group<0>();  // every output row has landed before the CTA exits
   } else {
     // ============================== softmax / correction / epilogue ==============================
     const int qt = (warp - 4) >> 3;         // query tile
@@ -551,7 +796,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
   }
 }
 
-template <bool kHasBias>
+template <bool kHasBias, int kGen>
 static int launch_attention64(const void* qkv, int64_t row_stride, int64_t batch_stride, int B, int T, int H,
                               const A64Params& p, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                               cudaStream_t stream) {
@@ -566,11 +811,11 @@ static int launch_attention64(const void* qkv, int64_t row_stride, int64_t batch
   {
     uint64_t dims[3] = {(uint64_t)H * 64, (uint64_t)T, (uint64_t)B};
     uint64_t strides[2] = {(uint64_t)out_row_stride * 2, (uint64_t)out_batch_stride * 2};
-    uint32_t box[3] = {64, 32, 1};
+    uint32_t box[3] = {64, kGen == 3 ? 16u : 32u, 1};  // rows one softmax warp stores
     int rc = make_tensor_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = attention64_kernel<kHasBias>;
+  auto kern = attention64_kernel<kHasBias, kGen>;
   static PerDeviceOnce configured;
   if (configured.needed()) {
     WFL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kA64Smem));
@@ -600,8 +845,11 @@ int attention64_dispatch(const void* qkv, int64_t row_stride, int64_t batch_stri
   p.rel_bias = rel_bias;
   p.gate = gate;
   if (rel_bias != nullptr)
-    return launch_attention64<true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride, stream);
-  return launch_attention64<false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride, stream);
+    return launch_attention64<true, 2>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride, stream);
+  static const char* gen = getenv("WFL_ATTN64_GEN");  // 2 = column-split softmax warps, 3 (default) = row-quad form
+  if (gen != nullptr && gen[0] == '2')
+    return launch_attention64<false, 2>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride, stream);
+  return launch_attention64<false, 3>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride, out_batch_stride, stream);
 }
 
 }  // namespace wfl
