@@ -147,6 +147,18 @@ __device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const uint32_
       : "memory");
 }
 // 16 registers starting at OFF of a 64-entry array -> 32 packed columns (.16x128b.x8) of the warp's 16 rows
+// the first 32 entries of a 64-entry array -> 64 packed columns (.16x128b.x16)
+__device__ __forceinline__ void tmem_st_16x128b_x16_lo(uint32_t taddr, const uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 template <int OFF>
 __device__ __forceinline__ void tmem_st_16x128b_x8_of64(uint32_t taddr, const uint32_t (&v)[64]) {
   asm volatile(
@@ -371,6 +383,26 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           const int stage = (g0 + j) % kA64Stages;
           MMA_WAIT(&v_full[stage], ((g0 + j) / kA64Stages) & 1);
           const uint32_t v_addr = v_addr0 + stage * kA64KvBytes;
+#if defined(WFL_A64_SINGLE_PV)
+          if constexpr (kGen == 3) {
+            // one product per tile: P arrives whole (the softmax warps store it once, after all exponentials)
+            MMA_WAIT(&p_full[qt * 2], (gq + j) & 1);
+            A64_TRACE(2);
+            if (j == 0 && m > 0) MMA_WAIT(&o_free[qt], (m - 1) & 1);
+            tc_fence_after();
+#ifdef WFL_A64_NOPV
+            if (false)
+#endif
+#pragma unroll
+            for (int k16 = 0; k16 < 8; ++k16) {
+              const uint64_t db = umma_smem_desc(v_addr + k16 * 2048, kA64KvBytes, 1024);
+              umma_f16_ts(tmem_base + kA64ColO + qt * 64, tmem_base + kA64ColP + qt * 64 + k16 * 8, db, idesc_pv,
+                          (j > 0 || k16 > 0) ? 1u : 0u);
+            }
+            umma_commit(&pv_done[qt * 2 + 1]);
+            A64_TRACE(3);
+          } else
+#endif
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             MMA_WAIT(&p_full[qt * 2 + sub], (gq + j) & 1);
@@ -495,6 +527,9 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
         }
         const uint64_t sc2 = pk2(sc, sc), negm0 = pk2(-m_used0, -m_used0), negm1 = pk2(-m_used1, -m_used1);
         uint64_t sum0 = pk2(0.f, 0.f), sum1 = pk2(0.f, 0.f);
+        // (Tried: a token -- two producer / consumer named barriers -- that makes the two query tiles take turns at the
+        // MUFU unit instead of falling into step, all sixteen warps in their exponentials together: 0.254 against
+        // 0.230 ms, the hand-overs cost more than the alternation gains.)
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           // keys [64 sub, 64 sub + 64): exponentials, packed IN PLACE (group gg: v[4gg..4gg+3] -> v[2gg], v[2gg+1])
@@ -502,11 +537,15 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           for (int g8 = 0; g8 < 8; ++g8) {
             const int gg = sub * 8 + g8;
             float a0, a1, a2, a3;
-            upk2(fma2(pk2u(v[4 * gg], v[4 * gg + 1]), sc2, negm0), a0, a1);
-            upk2(fma2(pk2u(v[4 * gg + 2], v[4 * gg + 3]), sc2, negm1), a2, a3);
+            const uint64_t x01 = fma2(pk2u(v[4 * gg], v[4 * gg + 1]), sc2, negm0);
+            const uint64_t x23 = fma2(pk2u(v[4 * gg + 2], v[4 * gg + 3]), sc2, negm1);
+            upk2(x01, a0, a1);
+            upk2(x23, a2, a3);
 #ifdef WFL_A64_NOEXP
             const float e0 = fmaf(a0, 1e-3f, 1.0f), e1 = fmaf(a1, 1e-3f, 1.0f), e2 = fmaf(a2, 1e-3f, 1.0f), e3 = fmaf(a3, 1e-3f, 1.0f);
 #else
+            // (every 8th / 4th / 2nd group through the FMA-pipe polynomial ex2_poly2 instead: 0.222 / 0.225 / 0.242 ms
+            // against 0.221 -- the MUFU unit is still not what bounds the kernel)
             const float e0 = ex2_ftz(a0), e1 = ex2_ftz(a1), e2 = ex2_ftz(a2), e3 = ex2_ftz(a3);
 #endif
             sum0 = add2(sum0, pk2(e0, e1));
@@ -515,6 +554,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
             v[2 * gg + 1] = pack_f16(e2, e3);
           }
           A64_TRACE(4 + sub * 2);
+#ifndef WFL_A64_SINGLE_PV
           // P_qt is single-buffered: the P V products of the previous tile must have retired before it is overwritten
           // (ONE wait covers both sub-blocks: they are issued in order by one thread); the first 64 keys' exponentials
           // above ran beside those products
@@ -531,7 +571,23 @@ attention64_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[qt * 2 + sub]);
           A64_TRACE(5 + sub * 2);
+#endif
         }
+#ifdef WFL_A64_SINGLE_PV
+        // A/B build: ONE store and one hand-over per tile instead of two (measured 0.221 against 0.215 ms for the split
+        // form: P V of the first 64 keys running beside the exponentials of the second 64 is worth more than the saved
+        // store / fence / arrive sequence)
+        if (g > 0) {
+          mbar_wait(&pv_done[qt * 2 + 1], (g - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_16x128b_x16_lo(p_addr, v);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[qt * 2]);
+        A64_TRACE(7);
+#endif
         float s0, s1, s2, s3;
         upk2(sum0, s0, s1);
         upk2(sum1, s2, s3);
