@@ -92,7 +92,10 @@ struct AttnParams {
 // kBiasSmem: the query tile's window of the relative-position table (T + 127 entries: row r of the tile, key k ->
 // entry k + 127 - r) is staged in shared memory behind the barriers once per CTA, so the per-score bias fetch is an
 // LDS at [row base + immediate] instead of a clamped LDG (0.198 -> see profiles/README.md at B 16 x H 16 x T 799).
-template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64, bool kBiasSmem = false>
+// kQuad: the two softmax warps of a 32-row TMEM quarter split its ROWS and read S in the 16-lane shape (a row = one quad
+// of lanes; common.cuh tmem_ld_16x256b_*): maxima and sums by shuffle -- no exchange buffer, no pair barrier -- like the
+// third generation of attention64.cu.
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64, bool kBiasSmem = false, bool kQuad = false>
 __global__ void __launch_bounds__(kAttnThreads, (AttnCfg<HD, KV_STAGES, kPTmem, KT>::kCtasPerSm))
 attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                  const __grid_constant__ CUtensorMap map_out, const AttnParams p) {
@@ -269,6 +272,169 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       } else {
         for (int j = 0; j < n_kv; ++j) issue_pv(j);
       }
+    }
+  } else if (warp >= 4 && kQuad) {
+    // ============================== softmax / correction / epilogue, row-quad form ==============================
+    if constexpr (kQuad) {
+    static_assert(!kQuad || (kPTmem && KT == 64), "the row-quad softmax is written for 64-key tiles with P in tensor memory");
+    const int quarter = warp & 3;             // TMEM lane quarter
+    const int rhalf = (warp - 4) >> 2;        // which 16 of the quarter's 32 rows
+    const int row_base = quarter * 32 + rhalf * 16;
+    const int r0 = row_base + (lane >> 2);    // this thread's first row inside the tile (the second is r0 + 8)
+    const int c0 = (lane & 3) * 2;            // its columns inside every 8-column group: c0, c0 + 1
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(row_base) << 16);
+    float gate0 = 0.f, gate1 = 0.f;           // gate * log2 e of the two rows
+    const float* brow0 = nullptr;             // bias of (row r0, key k) at brow0[k - c0 .. ]: see below
+    const float* brow1 = nullptr;
+    if constexpr (kHasBias) {
+      const int qa = q0 + r0 < p.T ? q0 + r0 : p.T - 1, qb = q0 + r0 + 8 < p.T ? q0 + r0 + 8 : p.T - 1;
+      const float* gp = p.gate + (static_cast<int64_t>(b) * p.H + h) * p.T;
+      gate0 = gp[qa] * kLog2e;
+      gate1 = gp[qb] * kLog2e;
+      if constexpr (kBiasSmem) {
+        // entry i of the window = table index (T - 1) - (q0 + 127) + i; rows past T and keys past T read zeros
+        const float* tab = p.rel_bias + static_cast<int64_t>(h) * (2 * p.T - 1);
+        const int first = (p.T - 1) - (q0 + 127);
+        const int n_tab = n_kv * KV_TILE + 128;
+        for (int i = threadIdx.x - 128; i < n_tab; i += kAttnThreads - 128) {
+          const int idx = first + i;
+          bias_tab[i] = (idx >= 0 && idx <= 2 * p.T - 2) ? __ldg(tab + idx) : 0.f;
+        }
+        asm volatile("bar.sync 6, 256;" ::: "memory");  // the eight softmax warps
+        brow0 = bias_tab + (127 - r0) + c0;  // + key index of the group's first column
+        brow1 = brow0 - 8;
+      } else {
+        brow0 = p.rel_bias + static_cast<int64_t>(h) * (2 * p.T - 1) + (p.T - 1 - qa);  // + key index (clamped)
+        brow1 = p.rel_bias + static_cast<int64_t>(h) * (2 * p.T - 1) + (p.T - 1 - qb);
+      }
+    }
+    const float sc = kHasBias ? 1.0f : p.scale_log2;
+    float m_used0 = -INFINITY, m_used1 = -INFINITY;
+    float l_sum0 = 0.f, l_sum1 = 0.f;  // this thread's columns only; the quad meets in the epilogue
+    for (int j = 0; j < n_kv; ++j) {
+      const int sb = j & 1;  // p_full / pv_done parity
+      const int ss = j % S_BUFS;
+      const uint32_t ss_phase = static_cast<uint32_t>((j / S_BUFS) & 1);
+      const int kv0 = j * KV_TILE;
+      mbar_wait(&s_full[ss], ss_phase);
+      tc_fence_after();
+      uint32_t v[32];  // v[4g + 0..1]: row r0, columns 8g + c0 + {0,1};  v[4g + 2..3]: row r0 + 8
+      tmem_ld_16x256b_x8(lane_addr + ss * KV_TILE, v);
+      tmem_ld_wait();
+      const bool tail = (j + 1) * KV_TILE > p.T;  // CTA-uniform
+      if constexpr (kHasBias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kk = kv0 + (i >> 2) * 8 + (i & 1);  // key index minus c0
+          float bv;
+          if constexpr (kBiasSmem) {
+            bv = (i & 2) ? brow1[kk] : brow0[kk];
+          } else {
+            const int k = min(kk + c0, p.T - 1);
+            bv = __ldg(((i & 2) ? brow1 : brow0) + k);
+          }
+          v[i] = __float_as_uint(fmaf((i & 2) ? gate1 : gate0, bv, __uint_as_float(v[i]) * p.scale_log2));
+        }
+      }
+      if (tail) {
+        const int valid = p.T - kv0 - c0;  // column 8g + (i & 1) of this thread is a key iff it is < valid
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if ((i >> 2) * 8 + (i & 1) >= valid) v[i] = 0xff800000u;  // -inf
+      }
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // [row][chain]
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        mx[g & 1] = fmaxf(mx[g & 1], fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])));
+        mx[2 + (g & 1)] = fmaxf(mx[2 + (g & 1)], fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+      }
+      float m0 = fmaxf(mx[0], mx[1]), m1 = fmaxf(mx[2], mx[3]);
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      const float m_new0 = fmaxf(m_used0, m0 * sc), m_new1 = fmaxf(m_used1, m1 * sc);
+      const bool grow0 = m_new0 > m_used0 + kRescaleThreshold, grow1 = m_new1 > m_used1 + kRescaleThreshold;
+      if (__any_sync(0xffffffffu, grow0 || grow1)) {  // also true on the first tile (m_used = -inf)
+        if (j > 0) {
+          // O holds sum_{i<j} P_i V_i scaled by 2^-m_used: rescale this warp's 16 rows once PV(j-1) retired
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          const float f0 = grow0 ? ex2_approx(m_used0 - m_new0) : 1.0f, f1 = grow1 ? ex2_approx(m_used1 - m_new1) : 1.0f;
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 32) {
+            uint32_t o[16];
+            tmem_ld_16x256b_x4(lane_addr + Cfg::kOCol + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * ((i & 2) ? f1 : f0));
+            tmem_st_16x256b_x4(lane_addr + Cfg::kOCol + c, o);
+          }
+          tmem_st_wait();
+          l_sum0 *= f0;
+          l_sum1 *= f1;
+        }
+        if (grow0) m_used0 = m_new0;
+        if (grow1) m_used1 = m_new1;
+      }
+      // PV(j-2) must have retired before this warp publishes P_j (it used the same p_full / pv_done pair, sb = j & 1; see
+      // the column-split form below for the race this wait closes)
+      if (j >= 2) mbar_wait(&pv_done[sb], ((j - 2) >> 1) & 1);
+      const uint64_t sc2 = pk2(sc, sc), negm0 = pk2(-m_used0, -m_used0), negm1 = pk2(-m_used1, -m_used1);
+      uint64_t sum0 = pk2(0.f, 0.f), sum1 = pk2(0.f, 0.f);
+      uint32_t pk[16];  // pk[2g] = row r0, packed column 4g + lane % 4;  pk[2g + 1] = row r0 + 8
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float a0, a1, a2, a3;
+        upk2(fma2(pk2u(v[4 * g], v[4 * g + 1]), sc2, negm0), a0, a1);
+        upk2(fma2(pk2u(v[4 * g + 2], v[4 * g + 3]), sc2, negm1), a2, a3);
+        const float e0 = ex2_approx(a0), e1 = ex2_approx(a1), e2 = ex2_approx(a2), e3 = ex2_approx(a3);
+        sum0 = add2(sum0, pk2(e0, e1));
+        sum1 = add2(sum1, pk2(e2, e3));
+        pk[2 * g] = pack_f16(e0, e1);
+        pk[2 * g + 1] = pack_f16(e2, e3);
+      }
+      // P overlays S buffer ss (this warp's rows only: nobody else reads them)
+      tmem_st_16x128b_x8(lane_addr + ss * KV_TILE, pk);
+      tmem_st_wait();
+      float s0, s1, s2, s3;
+      upk2(sum0, s0, s1);
+      upk2(sum1, s2, s3);
+      l_sum0 += s0 + s1;
+      l_sum1 += s2 + s3;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+    }
+    // ---- epilogue: O / l -> f16 -> (Q's smem, no longer needed) -> TMA store, 16 rows per warp
+    float l0 = l_sum0 + __shfl_xor_sync(0xffffffffu, l_sum0, 1), l1 = l_sum1 + __shfl_xor_sync(0xffffffffu, l_sum1, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+#pragma unroll 1
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t o[16];
+      tmem_ld_16x256b_x4(lane_addr + Cfg::kOCol + c, o);
+      tmem_ld_wait();
+      uint8_t* row0 = q_smem + (c >> 6) * (128 * 128) + r0 * 128 + (lane & 3) * 4;  // rows r0, r0 + 8: same swizzle phase
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int off = ((((c & 63) >> 3) + g) ^ (r0 & 7)) << 4;  // 16-byte chunk = 8 f16 columns
+        *reinterpret_cast<uint32_t*>(row0 + off) = pack_f16(__uint_as_float(o[4 * g]) * inv0, __uint_as_float(o[4 * g + 1]) * inv0);
+        *reinterpret_cast<uint32_t*>(row0 + 8 * 128 + off) =
+            pack_f16(__uint_as_float(o[4 * g + 2]) * inv1, __uint_as_float(o[4 * g + 3]) * inv1);
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && q0 + row_base < p.T) {
+      for (int jb = 0; jb < Cfg::kHdBlocks; ++jb)
+        tma_store_3d(&map_out, q_smem + jb * (128 * 128) + row_base * 128, h * HD + jb * 64, q0 + row_base, b);
+      tma_commit_group();
+      tma_wait_group<0>();
+    }
     }
   } else if (warp >= 4) {
     // ============================== softmax / correction / epilogue ==============================
@@ -494,7 +660,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 constexpr int kBiasSmemLimit = 113 * 1024;
 static int bias_window_bytes(int T, int KT) { return (((T + KT - 1) / KT) * KT + 128) * 4; }
 
-template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64, bool kBiasSmem = false>
+template <int HD, int KV_STAGES, bool kPTmem, bool kHasBias, int KT = 64, bool kBiasSmem = false, bool kQuad = false>
 static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_stride, int B, int T, int H,
                             const AttnParams& p, void* out, int64_t out_row_stride, int64_t out_batch_stride,
                             cudaStream_t stream) {
@@ -515,12 +681,12 @@ static int launch_attention(const void* qkv, int64_t row_stride, int64_t batch_s
   {
     uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)T, (uint64_t)B};
     uint64_t strides[2] = {(uint64_t)out_row_stride * 2, (uint64_t)out_batch_stride * 2};
-    uint32_t box[3] = {64, 32, 1};
+    uint32_t box[3] = {64, kQuad ? 16u : 32u, 1};  // rows one softmax warp stores
     int rc = make_tensor_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, dims, strides, box,
                              CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias, KT, kBiasSmem>;
+  auto kern = attention_kernel<HD, KV_STAGES, kPTmem, kHasBias, KT, kBiasSmem, kQuad>;
   const int smem_bytes = Cfg::kSmemBytes + (kBiasSmem ? bias_window_bytes(T, KT) : 0);
   static PerDeviceOnce configured;  // per instantiation and device
   if (configured.needed()) {
@@ -575,17 +741,37 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
       return attention64_dispatch(qkv, row_stride, batch_stride, q_col, k_col, v_col, B, T, H, scale, rel_bias, gate,
                                   out, out_row_stride, out_batch_stride, stream);
   }
+  // Row-quad softmax warps or the column-split form with its shared-memory exchange.  Measured on one box (tools/
+  // attn_v1_ab.sh): head dim 64 with bias 0.120 -> 0.108 ms (B 16, H 16, T 799) and 0.471 -> 0.415 ms (B 32, H 12, T 1499),
+  // plain 0.257 -> 0.238; head dim 256 / 384 are bound by the tensor pipe and do not move (0.171 -> 0.173, 0.554 ->
+  // 0.556) -- so the default is row-quad for head dim 64 only.  WFL_ATTN_V1_QUAD=0 / 1 forces one form everywhere (A/B).
+  static const int quad_env = [] {
+    const char* e = getenv("WFL_ATTN_V1_QUAD");
+    return e == nullptr ? -1 : (e[0] != '0' ? 1 : 0);
+  }();
+  const bool quad = hd == 64 ? quad_env != 0 : quad_env == 1;
   switch (hd) {
     case 64:
       if (rel_bias != nullptr) {
         // the table window in shared memory when it fits beside two resident CTAs (T <= ~11 000 frames = 230 s); the
         // choice depends on the clip length only, and both variants evaluate the same expression
-        if (AttnCfg<64, 3, true>::kSmemBytes + bias_window_bytes(T, 64) <= kBiasSmemLimit && getenv("WFL_ATTN_BIAS_LDG") == nullptr)
+        const bool window = AttnCfg<64, 3, true>::kSmemBytes + bias_window_bytes(T, 64) <= kBiasSmemLimit &&
+                            getenv("WFL_ATTN_BIAS_LDG") == nullptr;
+        if (window && quad)
+          return launch_attention<64, 3, true, true, 64, true, true>(qkv, row_stride, batch_stride, B, T, H, p, out,
+                                                                     out_row_stride, out_batch_stride, stream);
+        if (window)
           return launch_attention<64, 3, true, true, 64, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                                                out_batch_stride, stream);
+        if (quad)
+          return launch_attention<64, 3, true, true, 64, false, true>(qkv, row_stride, batch_stride, B, T, H, p, out,
+                                                                      out_row_stride, out_batch_stride, stream);
         return launch_attention<64, 3, true, true>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                                    out_batch_stride, stream);
       }
+      if (quad)
+        return launch_attention<64, 3, true, false, 64, false, true>(qkv, row_stride, batch_stride, B, T, H, p, out,
+                                                                     out_row_stride, out_batch_stride, stream);
       return launch_attention<64, 3, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                                   out_batch_stride, stream);
     case 256:
@@ -596,10 +782,16 @@ extern "C" int wfl_attention(const void* qkv, int64_t row_stride, int64_t batch_
       if (getenv("WFL_ATTN256_KT128") != nullptr)
         return launch_attention<256, 1, true, false, 128>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                                           out_batch_stride, stream);
+      if (quad)
+        return launch_attention<256, 2, true, false, 64, false, true>(qkv, row_stride, batch_stride, B, T, H, p, out,
+                                                                      out_row_stride, out_batch_stride, stream);
       return launch_attention<256, 2, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                                    out_batch_stride, stream);
     case 384:
       if (rel_bias != nullptr) break;
+      if (quad)
+        return launch_attention<384, 1, true, false, 64, false, true>(qkv, row_stride, batch_stride, B, T, H, p, out,
+                                                                      out_row_stride, out_batch_stride, stream);
       return launch_attention<384, 1, true, false>(qkv, row_stride, batch_stride, B, T, H, p, out, out_row_stride,
                                             out_batch_stride, stream);
     default:
