@@ -232,7 +232,9 @@ def _attn_ref(qkv, B, T, H, hd, scale, bias=None):
                                        (64, 2, 256, 1), (64, 2, 257, 2), (64, 3, 384, 1), (64, 2, 385, 1), (64, 12, 499, 2),
                                        (64, 16, 799, 1),
                                        # more 256-row items than SMs, every fourth one without a second query tile
-                                       (64, 16, 799, 16), (64, 8, 640, 40)])
+                                       (64, 16, 799, 16), (64, 8, 640, 40),
+                                       # sequence ends inside / at the edge of a softmax warp's 16-row block
+                                       (64, 2, 5, 1), (64, 2, 16, 2), (64, 2, 17, 1), (64, 2, 31, 2), (64, 2, 47, 1), (64, 2, 143, 1)])
 def test_attention(hd, H, T, B):
     d = H * hd
     qkv = _rand(B, T, 3 * d, seed=23).half()
@@ -247,7 +249,9 @@ def test_attention(hd, H, T, B):
 @pytest.mark.parametrize("hd,H,T,B,bias", [(64, 2, 128, 1, False), (64, 3, 300, 2, False), (64, 8, 1500, 1, False), (64, 2, 1, 2, False),
                                             (64, 1, 65, 1, False), (64, 4, 129, 3, False), (64, 2, 256, 1, False),
                                             (64, 2, 257, 2, False), (64, 3, 384, 1, False), (64, 2, 385, 1, False),
-                                            (64, 12, 499, 2, True), (64, 16, 799, 4, True), (64, 16, 799, 16, False)])
+                                            (64, 12, 499, 2, True), (64, 16, 799, 4, True), (64, 16, 799, 16, False),
+                                            (64, 2, 5, 1, True), (64, 2, 17, 2, True), (64, 2, 31, 1, True), (64, 2, 47, 1, False),
+                                            (64, 2, 143, 2, True)])
 def test_attention_hd64_both_generations(monkeypatch, gen, hd, H, T, B, bias):
     """head_dim 64 has two kernels (attention.cu: 128-row CTAs, 64-key tiles; attention64.cu: persistent 256-row items,
     128-key tiles) chosen by problem size; WFL_ATTN64 forces each of them over the same edge shapes (second query tile
