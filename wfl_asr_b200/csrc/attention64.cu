@@ -31,7 +31,10 @@ namespace wfl {
 
 constexpr int kA64Threads = 640;
 constexpr int kA64Kv = 128;      // keys per tile
-constexpr int kA64Stages = 3;    // K and V ring depth
+#ifndef WFL_A64_STAGES
+#define WFL_A64_STAGES 3
+#endif
+constexpr int kA64Stages = WFL_A64_STAGES;    // K and V ring depth (2, 3 and 4 measure the same: tools/a64_ab.sh)
 constexpr int kA64QTile = 128 * 64 * 2;   // one query tile, bytes
 constexpr int kA64KvBytes = kA64Kv * 64 * 2;
 constexpr int kA64Xchg = 2 * 2 * 2 * 128 * 4;  // row-max exchange [query tile][tile parity][column half][row]
